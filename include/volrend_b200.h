@@ -1,0 +1,150 @@
+/*
+ * volrend_b200.h -- thin C-ABI of the B200-native PlenOctree ray-marcher.
+ *
+ * This is the drop-in boundary for volrend's CUDA backend (reference paths relative to
+ * /root/reference).  Everything the reference's `src/cuda/*` exports is re-expressed
+ * here with plain pointers and sizes -- no torch, glm, cnpy or CUDA types:
+ *
+ *   vr_tree_create / vr_tree_destroy   replace N3Tree::load_cuda / free_cuda
+ *                                      (src/cuda/n3tree.cu:9-41, :43-49; the struct
+ *                                      N3Tree::device, include/volrend/n3tree.hpp:72-78)
+ *   vr_render                          replaces launch_renderer(..., offscreen=true)
+ *                                      (include/volrend/cuda/renderer_kernel.hpp:9-12,
+ *                                      src/cuda/volrend.cu:195-245) and the device side
+ *                                      render_kernel (volrend.cu:78-173) + trace_ray
+ *                                      (include/volrend/cuda/rt_core.cuh:66-196)
+ *   vr_render_composite                replaces launch_renderer(..., offscreen=false):
+ *                                      colour + depth inputs (volrend.cu:92-96,143-146)
+ *   vr_render_batch                    the per-pose loop of main_headless.cpp:208-223 as
+ *                                      one call (same per-view semantics)
+ *   vr_render_frames_host              main_headless.cpp:208-223 with `-o`: renders and
+ *                                      copies every frame to host memory (:216-219)
+ *   vr_probe_lumisphere                retrieve_cursor_lumisphere_kernel (volrend.cu:175-191)
+ *   vr_last_error                      replaces the abort-on-error cuda_assert
+ *                                      (src/cuda/common.cu:8-21) -- the C-ABI never aborts;
+ *                                      the C++ shim (volrend_b200/csrc/shim) restores it.
+ *
+ * All calls return 0 on success or a negative VR_E* code; vr_last_error() gives the text.
+ * Device buffers are caller-owned; rendering is asynchronous on the given CUDA stream
+ * (passed as void* == cudaStream_t).  One vr_tree lives on the device that was current at
+ * creation.  There is NO CPU fallback: without a CUDA device every call fails with
+ * VR_ENODEVICE.
+ */
+#ifndef VOLREND_B200_H_
+#define VOLREND_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VR_BASIS_MAX 25 /* VOLREND_GLOBAL_BASIS_MAX, include/volrend/render_options.hpp:6 */
+
+enum { VR_OK = 0, VR_EINVAL = -1, VR_ENODEVICE = -2, VR_ECUDA = -3, VR_ENOMEM = -4, VR_EUNSUPPORTED = -5 };
+
+/* DataFormat::format, include/volrend/data_format.hpp:9-15 */
+enum { VR_FMT_RGBA = 0, VR_FMT_SH = 1, VR_FMT_SG = 2, VR_FMT_ASG = 3 };
+
+typedef struct vr_tree vr_tree; /* opaque: re-laid-out device copy of one N3Tree */
+
+/* Host-side view of a loaded N3Tree (fields of include/volrend/n3tree.hpp:33-85). */
+typedef struct {
+    const int32_t* child;   /* N3Tree::child_  int32 [capacity*N^3], relative offsets, 0 = leaf */
+    const uint16_t* data;   /* N3Tree::data_   fp16  [capacity*N^3*data_dim] */
+    const float* extra;     /* N3Tree::extra_  SG: [basis_dim*4], ASG: [basis_dim*11], else NULL */
+    int64_t capacity;       /* N3Tree::capacity */
+    int32_t N;              /* N3Tree::N (only 2 is supported, as in the reference) */
+    int32_t data_dim;       /* N3Tree::data_dim */
+    int32_t format;         /* N3Tree::data_format.format (VR_FMT_*) */
+    int32_t basis_dim;      /* N3Tree::data_format.basis_dim (-1 for RGBA) */
+    float offset[3];        /* N3Tree::offset */
+    float scale[3];         /* N3Tree::scale */
+    int32_t use_ndc;        /* N3Tree::use_ndc */
+    float ndc_width, ndc_height, ndc_focal;
+} vr_tree_desc;
+
+/* Camera (include/volrend/camera.hpp:31-48); c2w by value, no device copy needed. */
+typedef struct {
+    int32_t width, height;
+    float fx, fy;
+    float c2w[12];          /* glm::mat4x3 Camera::transform, column-major */
+} vr_camera;
+
+/* RenderOptions (include/volrend/render_options.hpp:11-53), ray-march subset. */
+typedef struct {
+    float step_size, sigma_thresh, stop_thresh, background_brightness;
+    float render_bbox[6];
+    int32_t basis_minmax[2];
+    float rot_dirs[3];
+    int32_t render_depth;
+} vr_options;
+
+typedef struct { int32_t x0, y0, w, h; } vr_rect;
+
+/* Work counters (device-resident, accumulated with atomics when requested). */
+typedef struct {
+    unsigned long long samples;      /* S        march-loop iterations (rt_core.cuh:108) */
+    unsigned long long child_loads;  /* sum d_s  child[] reads the reference algorithm makes */
+    unsigned long long shaded;       /* S_shaded samples with sigma > sigma_thresh */
+    unsigned long long rays_hit;     /* rays entering the march */
+    unsigned long long node_fetches; /* node words this implementation actually loaded */
+} vr_counters;
+
+typedef struct {
+    int64_t capacity;
+    int32_t max_depth;               /* deepest leaf (root children = 1) */
+    int32_t rec_bytes;               /* padded leaf-record stride */
+    int64_t node_bytes, rec_total_bytes, top_bytes;
+} vr_tree_info;
+
+void vr_default_options(vr_options* o);
+
+int vr_tree_create(const vr_tree_desc* desc, vr_tree** out);
+void vr_tree_destroy(vr_tree* tree);
+int vr_tree_get_info(const vr_tree* tree, vr_tree_info* info);
+
+/* Offscreen render of `tile` (NULL = full frame) of view `cam`.  rgba8_dev: tile-sized
+ * linear RGBA8 (pitch 4*tile.w) or NULL; rgba32f_dev: tile-sized float4 or NULL;
+ * counters_dev: device vr_counters to accumulate into, or NULL. */
+int vr_render(const vr_tree* tree, const vr_camera* cam, const vr_options* opt, const vr_rect* tile,
+              uint8_t* rgba8_dev, float* rgba32f_dev, vr_counters* counters_dev, void* stream);
+
+/* n_views cameras (host array), outputs are n_views consecutive tile-sized images. */
+int vr_render_batch(const vr_tree* tree, const vr_camera* cams, int n_views, const vr_options* opt,
+                    const vr_rect* tile, uint8_t* rgba8_dev, float* rgba32f_dev,
+                    vr_counters* counters_dev, void* stream);
+
+/* launch_renderer(offscreen=false): rgba8_dev is read (existing colour) and overwritten;
+ * depth_dev holds the per-pixel ray-distance limit (world units), both tile-sized. */
+int vr_render_composite(const vr_tree* tree, const vr_camera* cam, const vr_options* opt,
+                        const vr_rect* tile, uint8_t* rgba8_dev, const float* depth_dev,
+                        float* rgba32f_dev, void* stream);
+
+/* Same, writing a CUDA surface object over an RGBA8 cudaArray (what the reference's
+ * caller owns, main_headless.cpp:190-199); depth_surf = 0 => offscreen. */
+int vr_render_surface(const vr_tree* tree, const vr_camera* cam, const vr_options* opt,
+                      unsigned long long rgba8_surf, unsigned long long depth_surf, void* stream);
+
+/* Host-buffer entry point: renders n_views full frames and copies each to
+ * rgba8_host + i*4*w*h (pinned or pageable); returns after the last copy completed. */
+int vr_render_frames_host(const vr_tree* tree, const vr_camera* cams, int n_views,
+                          const vr_options* opt, uint8_t* rgba8_host);
+
+/* Copies the (data_dim-1) coefficients of the leaf containing world point xyz into
+ * out_dev as floats (retrieve_cursor_lumisphere_kernel). */
+int vr_probe_lumisphere(const vr_tree* tree, const float xyz_world[3], float* out_dev, void* stream);
+
+/* Kernel variant selection for measurement (0 = default/best). */
+int vr_set_variant(int variant);
+int vr_get_variant(void);
+/* How many of this library's kernels were launched by this process. */
+unsigned long long vr_launch_count(void);
+
+const char* vr_last_error(void);
+const char* vr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

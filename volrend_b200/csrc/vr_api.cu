@@ -1,0 +1,513 @@
+// vr_api.cu -- C-ABI of the B200 PlenOctree ray-marcher (declared in include/volrend_b200.h).
+//
+// Owns the device layout of a tree (the job of N3Tree::load_cuda, reference
+// src/cuda/n3tree.cu:9-41) and the launch logic (launch_renderer, src/cuda/volrend.cu:195-245).
+// There is no CPU path in this library: every entry point needs a CUDA device.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "volrend_b200.h"
+#include "vr_kernels.h"
+#include "vr_types.h"
+
+using namespace vrb;
+
+// ------------------------------------------------------------------------------------ errors
+namespace {
+thread_local std::string g_err;
+std::atomic<int> g_variant{0};
+std::atomic<unsigned long long> g_launches{0};
+constexpr int kDefaultVariant = 4;
+constexpr int kQueueSlots = 256;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define VR_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(e__ == cudaErrorMemoryAllocation ? VR_ENOMEM : VR_ECUDA, "%s: %s (%s:%d)", \
+                        #expr, cudaGetErrorString(e__), __FILE__, __LINE__);                       \
+    } while (0)
+
+int kernel_basis(int format, int basis_dim) {
+    if (format == VR_FMT_RGBA || basis_dim < 0) return -1;
+    switch (basis_dim) {
+        case 1: case 4: case 9: case 16: case 25: return basis_dim;
+        default: return 1;  // rt_core.cuh:134-160: no switch case matches -> only coefficient 0
+    }
+}
+int rec_bytes_for(int kbd) { return kbd <= 1 ? 8 : ((3 * kbd * 2 + 15) / 16) * 16; }
+}  // namespace
+
+struct vr_tree {
+    int device = 0;
+    int num_sms = 0;
+    TreeDev dev{};
+    uint32_t* nodes = nullptr;
+    unsigned char* recs = nullptr;
+    uint32_t* top = nullptr;
+    float* extra = nullptr;
+    unsigned int* queues = nullptr;  // kQueueSlots x {head, done}
+    std::atomic<unsigned int> next_queue{0};
+    vr_tree_info info{};
+    int data_dim = 0;
+};
+
+// ------------------------------------------------------------------------------------ re-layout kernels
+namespace {
+
+// nodes[i]: absolute child id, or leaf bit | sigma.  Also validates child links.
+__global__ void relayout_nodes_kernel(const int32_t* __restrict__ child, const unsigned short* __restrict__ data,
+                                      uint32_t* __restrict__ nodes, long long n_slots, long long capacity,
+                                      int data_dim, int* __restrict__ bad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    const int32_t rel = child[i];
+    if (rel != 0) {
+        const long long tgt = (i >> 3) + rel;
+        if (tgt <= 0 || tgt >= capacity) {
+            atomicExch(bad, 1);
+            nodes[i] = kLeafBit;
+        } else {
+            nodes[i] = (uint32_t)tgt;
+        }
+    } else {
+        nodes[i] = kLeafBit | (uint32_t)data[(size_t)i * data_dim + (data_dim - 1)];
+    }
+}
+
+// recs[i]: colour coefficients of slot i, padded.  One thread per (slot, 16-byte chunk).
+__global__ void relayout_recs_kernel(const unsigned short* __restrict__ data, unsigned char* __restrict__ recs,
+                                     long long n_slots, int data_dim, int basis_dim, int kbd, int rec_bytes) {
+    const int chunks = rec_bytes >= 16 ? rec_bytes / 16 : 1;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long slot = gid / chunks;
+    const int chunk = (int)(gid % chunks);
+    if (slot >= n_slots) return;
+    const unsigned short* src = data + (size_t)slot * data_dim;
+    if (rec_bytes == 8) {
+        // one coefficient per channel: RGBA -> halfs 0,1,2 ; basis -> k[0], k[bd], k[2bd]
+        const int stride = kbd < 0 ? 1 : basis_dim;
+        ushort4 v;
+        v.x = src[0]; v.y = src[stride]; v.z = src[2 * stride]; v.w = 0;
+        reinterpret_cast<ushort4*>(recs)[slot] = v;
+        return;
+    }
+    const int n_coef = 3 * kbd;
+    unsigned short h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = chunk * 8 + j;
+        h[j] = c < n_coef ? src[c] : (unsigned short)0;
+    }
+    uint4 v;
+    v.x = h[0] | ((uint32_t)h[1] << 16); v.y = h[2] | ((uint32_t)h[3] << 16);
+    v.z = h[4] | ((uint32_t)h[5] << 16); v.w = h[6] | ((uint32_t)h[7] << 16);
+    reinterpret_cast<uint4*>(recs + (size_t)slot * rec_bytes)[chunk] = v;
+}
+
+// depth[n] of every node by level-synchronous relaxation from the root.
+__global__ void node_depth_kernel(const uint32_t* __restrict__ nodes, int* __restrict__ depth, long long capacity,
+                                  int level, int* __restrict__ changed) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= capacity || depth[n] != level) return;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const uint32_t w = nodes[n * 8 + s];
+        if (!(w & kLeafBit)) {
+            depth[w] = level + 1;
+            *changed = 1;
+        }
+    }
+}
+
+// top[cell]: leaf word (bit31 | depth<<28 | sigma) or the depth-4 node id.
+__global__ void build_top_kernel(const uint32_t* __restrict__ nodes, uint32_t* __restrict__ top) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= kTopCells) return;
+    const uint32_t cx = (cell >> 8) & 15, cy = (cell >> 4) & 15, cz = cell & 15;
+    uint32_t node = 0;
+    for (int l = 1; l <= kTopLevel; ++l) {
+        const int sh = kTopLevel - l;
+        const uint32_t oct = (((cx >> sh) & 1u) << 2) | (((cy >> sh) & 1u) << 1) | ((cz >> sh) & 1u);
+        const uint32_t w = nodes[node * 8u + oct];
+        if (w & kLeafBit) {
+            top[cell] = kLeafBit | ((uint32_t)l << 28) | (w & 0xffffu);
+            return;
+        }
+        node = w;
+    }
+    top[cell] = node;
+}
+
+__global__ void probe_kernel(TreeDev tree, float x, float y, float z, int n_out, float* __restrict__ out) {
+    // retrieve_cursor_lumisphere_kernel (volrend.cu:175-191)
+    float p[3] = {tree.offset[0] + tree.scale[0] * x, tree.offset[1] + tree.scale[1] * y,
+                  tree.offset[2] + tree.scale[2] * z};
+    uint32_t u[3];
+    for (int i = 0; i < 3; ++i) {
+        p[i] = fmaxf(fminf(p[i], 1.f - 1e-6f), 0.f);
+        u[i] = __float2uint_rz(p[i] * 16777216.f);
+    }
+    uint32_t node = 0, idx = 0;
+    for (int l = 0;; ++l) {
+        const int sh = 23 - l;
+        const uint32_t oct = (((u[0] >> sh) & 1u) << 2) | (((u[1] >> sh) & 1u) << 1) | ((u[2] >> sh) & 1u);
+        idx = node * 8u + oct;
+        const uint32_t w = tree.nodes[idx];
+        if (w & kLeafBit) break;
+        node = w;
+    }
+    const unsigned short* rec = reinterpret_cast<const unsigned short*>(tree.recs + (size_t)idx * tree.rec_bytes);
+    for (int i = threadIdx.x; i < n_out; i += blockDim.x) out[i] = __half2float(__ushort_as_half(rec[i]));
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ C-ABI
+extern "C" {
+
+const char* vr_last_error(void) { return g_err.c_str(); }
+const char* vr_version(void) { return "volrend_b200 0.1 (sm_100a)"; }
+int vr_set_variant(int variant) {
+    if (variant < 0 || variant > 4) return fail(VR_EINVAL, "variant must be 0..4");
+    g_variant.store(variant);
+    return VR_OK;
+}
+int vr_get_variant(void) {
+    const int v = g_variant.load();
+    return v == 0 ? kDefaultVariant : v;
+}
+unsigned long long vr_launch_count(void) { return g_launches.load(); }
+
+void vr_default_options(vr_options* o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->step_size = 1e-4f; o->sigma_thresh = 1e-2f; o->stop_thresh = 1e-2f;  // render_options.hpp:14-23
+    o->background_brightness = 1.f;
+    o->render_bbox[3] = o->render_bbox[4] = o->render_bbox[5] = 1.f;
+    o->basis_minmax[0] = 0; o->basis_minmax[1] = VR_BASIS_MAX - 1;
+}
+
+void vr_tree_destroy(vr_tree* t) {
+    if (!t) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(t->device);
+    cudaFree(t->nodes); cudaFree(t->recs); cudaFree(t->top); cudaFree(t->extra); cudaFree(t->queues);
+    cudaSetDevice(prev);
+    delete t;
+}
+
+int vr_tree_create(const vr_tree_desc* d, vr_tree** out) {
+    if (!d || !out) return fail(VR_EINVAL, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(VR_ENODEVICE, "no CUDA device: volrend_b200 has no CPU fallback");
+    }
+    if (d->N != 2) return fail(VR_EUNSUPPORTED, "N=%d: only N=2 octrees are supported (as in the reference)", d->N);
+    if (d->capacity < 1 || d->capacity >= (1ll << 28)) return fail(VR_EINVAL, "capacity %lld out of range", (long long)d->capacity);
+    if (!d->child || !d->data) return fail(VR_EINVAL, "child/data arrays missing");
+    if (d->format < VR_FMT_RGBA || d->format > VR_FMT_ASG) return fail(VR_EINVAL, "bad data format %d", d->format);
+    const int kbd = kernel_basis(d->format, d->basis_dim);
+    if (kbd < 0 ? d->data_dim < 4 : d->data_dim < 3 * d->basis_dim + 1)
+        return fail(VR_EINVAL, "data_dim %d too small for format %d basis %d", d->data_dim, d->format, d->basis_dim);
+    if ((d->format == VR_FMT_SG || d->format == VR_FMT_ASG) && !d->extra)
+        return fail(VR_EINVAL, "SG/ASG trees need extra_data");
+    if ((d->format == VR_FMT_SG || d->format == VR_FMT_ASG) && d->basis_dim > VR_BASIS_MAX)
+        return fail(VR_EINVAL, "basis_dim %d > %d", d->basis_dim, VR_BASIS_MAX);
+
+    vr_tree* t = new vr_tree();
+    struct Guard { vr_tree*& t; bool ok = false; ~Guard() { if (!ok) { vr_tree_destroy(t); t = nullptr; } } } guard{t};
+    VR_CUDA(cudaGetDevice(&t->device));
+    cudaDeviceProp prop;
+    VR_CUDA(cudaGetDeviceProperties(&prop, t->device));
+    t->num_sms = prop.multiProcessorCount;
+    t->data_dim = d->data_dim;
+    const long long n_slots = d->capacity * 8;
+    const int rec_bytes = rec_bytes_for(kbd);
+
+    int32_t* raw_child = nullptr;
+    unsigned short* raw_data = nullptr;
+    int* flags = nullptr;
+    int* depth = nullptr;
+    struct Tmp { int32_t*& a; unsigned short*& b; int*& c; int*& d; ~Tmp() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); } } tmp{raw_child, raw_data, flags, depth};
+    const size_t child_bytes = (size_t)n_slots * 4, data_bytes = (size_t)n_slots * d->data_dim * 2;
+    VR_CUDA(cudaMalloc(&raw_child, child_bytes));
+    VR_CUDA(cudaMalloc(&raw_data, data_bytes));
+    VR_CUDA(cudaMalloc(&flags, 2 * sizeof(int)));
+    VR_CUDA(cudaMalloc(&depth, (size_t)d->capacity * sizeof(int)));
+    VR_CUDA(cudaMalloc(&t->nodes, (size_t)n_slots * 4));
+    VR_CUDA(cudaMalloc(&t->recs, (size_t)n_slots * rec_bytes));
+    VR_CUDA(cudaMalloc(&t->top, kTopCells * 4));
+    VR_CUDA(cudaMalloc(&t->queues, kQueueSlots * 2 * sizeof(unsigned int)));
+    VR_CUDA(cudaMemset(t->queues, 0, kQueueSlots * 2 * sizeof(unsigned int)));
+    VR_CUDA(cudaMemcpy(raw_child, d->child, child_bytes, cudaMemcpyHostToDevice));
+    VR_CUDA(cudaMemcpy(raw_data, d->data, data_bytes, cudaMemcpyHostToDevice));
+    VR_CUDA(cudaMemset(flags, 0, 2 * sizeof(int)));
+    if (d->extra && (d->format == VR_FMT_SG || d->format == VR_FMT_ASG)) {
+        const size_t nf = (size_t)d->basis_dim * (d->format == VR_FMT_SG ? 4 : 11);
+        VR_CUDA(cudaMalloc(&t->extra, nf * sizeof(float)));
+        VR_CUDA(cudaMemcpy(t->extra, d->extra, nf * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    const int TB = 256;
+    relayout_nodes_kernel<<<(unsigned)((n_slots + TB - 1) / TB), TB>>>(raw_child, raw_data, t->nodes, n_slots,
+                                                                       d->capacity, d->data_dim, flags);
+    {
+        const long long work = n_slots * (rec_bytes >= 16 ? rec_bytes / 16 : 1);
+        relayout_recs_kernel<<<(unsigned)((work + TB - 1) / TB), TB>>>(raw_data, t->recs, n_slots, d->data_dim,
+                                                                       d->basis_dim, kbd, rec_bytes);
+    }
+    VR_CUDA(cudaGetLastError());
+    int h_flags[2] = {0, 0};
+    VR_CUDA(cudaMemcpy(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost));
+    if (h_flags[0]) return fail(VR_EINVAL, "child array has links outside [1, capacity)");
+    // node depths -> max leaf depth
+    VR_CUDA(cudaMemset(depth, 0xff, (size_t)d->capacity * sizeof(int)));
+    VR_CUDA(cudaMemset(depth, 0, sizeof(int)));
+    int max_node_depth = 0;
+    for (int level = 0;; ++level) {
+        if (level >= kMaxTreeDepth) return fail(VR_EUNSUPPORTED, "tree deeper than %d levels", kMaxTreeDepth);
+        VR_CUDA(cudaMemset(flags + 1, 0, sizeof(int)));
+        node_depth_kernel<<<(unsigned)((d->capacity + TB - 1) / TB), TB>>>(t->nodes, depth, d->capacity, level, flags + 1);
+        int changed = 0;
+        VR_CUDA(cudaMemcpy(&changed, flags + 1, sizeof(int), cudaMemcpyDeviceToHost));
+        if (!changed) break;
+        max_node_depth = level + 1;
+    }
+    build_top_kernel<<<(kTopCells + TB - 1) / TB, TB>>>(t->nodes, t->top);
+    VR_CUDA(cudaGetLastError());
+    VR_CUDA(cudaDeviceSynchronize());
+    g_launches += 4;
+
+    TreeDev& D = t->dev;
+    D.nodes = t->nodes; D.recs = t->recs; D.top = t->top; D.extra = t->extra;
+    for (int i = 0; i < 3; ++i) { D.offset[i] = d->offset[i]; D.scale[i] = d->scale[i]; }
+    D.ndc_width = d->use_ndc ? d->ndc_width : -1.f;  // data_spec.hpp:47
+    D.ndc_height = d->ndc_height; D.ndc_focal = d->ndc_focal;
+    D.N = d->N; D.format = d->format; D.basis_dim = d->basis_dim; D.kbd = kbd;
+    D.rec_bytes = rec_bytes; D.max_depth = max_node_depth + 1;
+    t->info.capacity = d->capacity; t->info.max_depth = D.max_depth; t->info.rec_bytes = rec_bytes;
+    t->info.node_bytes = n_slots * 4; t->info.rec_total_bytes = n_slots * (long long)rec_bytes;
+    t->info.top_bytes = kTopCells * 4;
+    guard.ok = true;
+    *out = t;
+    return VR_OK;
+}
+
+int vr_tree_get_info(const vr_tree* t, vr_tree_info* info) {
+    if (!t || !info) return fail(VR_EINVAL, "null argument");
+    *info = t->info;
+    return VR_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------ launch plumbing
+namespace {
+
+void fill_opt(OptDev& o, const vr_options* s) {
+    o.step_size = s->step_size; o.sigma_thresh = s->sigma_thresh; o.stop_thresh = s->stop_thresh;
+    o.background_brightness = s->background_brightness;
+    for (int i = 0; i < 6; ++i) o.render_bbox[i] = s->render_bbox[i];
+    o.basis_min = s->basis_minmax[0]; o.basis_max = s->basis_minmax[1];
+    for (int i = 0; i < 3; ++i) o.rot_dirs[i] = s->rot_dirs[i];
+    o.render_depth = s->render_depth;
+}
+void fill_cam(CamDev& c, const vr_camera* s) {
+    c.width = s->width; c.height = s->height; c.fx = s->fx; c.fy = s->fy;
+    memcpy(c.c2w, s->c2w, sizeof(c.c2w));
+}
+
+int dispatch(const vr_tree* t, LaunchDev& P, bool count, bool surface, cudaStream_t stream) {
+    LaunchCfg cfg;
+    cfg.variant = vr_get_variant();
+    cfg.count = count; cfg.surface = surface; cfg.num_sms = t->num_sms; cfg.stream = stream;
+    vr_tree* mt = const_cast<vr_tree*>(t);
+    cfg.queue = mt->queues + 2 * (mt->next_queue.fetch_add(1) % kQueueSlots);
+    cudaError_t e;
+    switch (t->dev.kbd) {
+        case -1: e = launch_march<-1>(P, cfg); break;
+        case 1: e = launch_march<1>(P, cfg); break;
+        case 4: e = launch_march<4>(P, cfg); break;
+        case 9: e = launch_march<9>(P, cfg); break;
+        case 16: e = launch_march<16>(P, cfg); break;
+        case 25: e = launch_march<25>(P, cfg); break;
+        default: return fail(VR_EUNSUPPORTED, "unsupported kernel basis %d", t->dev.kbd);
+    }
+    if (e != cudaSuccess) return fail(VR_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    g_launches += 1;
+    return VR_OK;
+}
+
+int check_common(const vr_tree* t, const vr_camera* cam, const vr_options* opt, const vr_rect* tile, vr_rect& r) {
+    if (!t || !cam || !opt) return fail(VR_EINVAL, "null argument");
+    if (cam->width <= 0 || cam->height <= 0) return fail(VR_EINVAL, "bad camera size %dx%d", cam->width, cam->height);
+    if (tile) {
+        r = *tile;
+        if (r.w < 0 || r.h < 0 || r.x0 < 0 || r.y0 < 0 || r.x0 + r.w > cam->width || r.y0 + r.h > cam->height)
+            return fail(VR_EINVAL, "tile (%d,%d,%d,%d) outside %dx%d frame", r.x0, r.y0, r.w, r.h, cam->width, cam->height);
+    } else {
+        r.x0 = r.y0 = 0; r.w = cam->width; r.h = cam->height;
+    }
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(VR_ENODEVICE, "no CUDA device");
+    if (dev != t->device) return fail(VR_EINVAL, "tree lives on device %d but device %d is current", t->device, dev);
+    return VR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vr_render_batch(const vr_tree* t, const vr_camera* cams, int n_views, const vr_options* opt, const vr_rect* tile,
+                    uint8_t* rgba8_dev, float* rgba32f_dev, vr_counters* counters_dev, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_views < 0) return fail(VR_EINVAL, "n_views < 0");
+    if (n_views == 0) return VR_OK;
+    vr_rect r;
+    int rc = check_common(t, cams, opt, tile, r);
+    if (rc) return rc;
+    for (int i = 1; i < n_views; ++i)
+        if (cams[i].width != cams[0].width || cams[i].height != cams[0].height)
+            return fail(VR_EINVAL, "all views of a batch must share one image size");
+    if (r.w == 0 || r.h == 0) return VR_OK;
+    LaunchDev P{};
+    P.tree = t->dev;
+    fill_opt(P.opt, opt);
+    fill_cam(P.cam, &cams[0]);
+    P.n_views = n_views;
+    P.x0 = r.x0; P.y0 = r.y0; P.w = r.w; P.h = r.h;
+    P.rgba8 = rgba8_dev; P.rgbaf = reinterpret_cast<float4*>(rgba32f_dev);
+    P.counters = counters_dev;
+    CamDev* dcams = nullptr;
+    if (n_views > 1) {
+        std::vector<CamDev> h(n_views);
+        for (int i = 0; i < n_views; ++i) fill_cam(h[i], &cams[i]);
+        VR_CUDA(cudaMallocAsync(&dcams, sizeof(CamDev) * n_views, stream));
+        VR_CUDA(cudaMemcpyAsync(dcams, h.data(), sizeof(CamDev) * n_views, cudaMemcpyHostToDevice, stream));
+        // pageable source: the copy has been staged when cudaMemcpyAsync returns
+        P.cams = dcams;
+    }
+    rc = dispatch(t, P, counters_dev != nullptr, false, stream);
+    if (dcams) cudaFreeAsync(dcams, stream);
+    return rc;
+}
+
+int vr_render(const vr_tree* t, const vr_camera* cam, const vr_options* opt, const vr_rect* tile, uint8_t* rgba8_dev,
+              float* rgba32f_dev, vr_counters* counters_dev, void* stream) {
+    return vr_render_batch(t, cam, 1, opt, tile, rgba8_dev, rgba32f_dev, counters_dev, stream);
+}
+
+int vr_render_composite(const vr_tree* t, const vr_camera* cam, const vr_options* opt, const vr_rect* tile,
+                        uint8_t* rgba8_dev, const float* depth_dev, float* rgba32f_dev, void* stream_) {
+    vr_rect r;
+    int rc = check_common(t, cam, opt, tile, r);
+    if (rc) return rc;
+    if (!rgba8_dev || !depth_dev) return fail(VR_EINVAL, "composite mode needs colour and depth inputs");
+    if (r.w == 0 || r.h == 0) return VR_OK;
+    LaunchDev P{};
+    P.tree = t->dev;
+    fill_opt(P.opt, opt);
+    fill_cam(P.cam, cam);
+    P.n_views = 1;
+    P.x0 = r.x0; P.y0 = r.y0; P.w = r.w; P.h = r.h;
+    P.rgba8 = rgba8_dev; P.rgbaf = reinterpret_cast<float4*>(rgba32f_dev);
+    P.depth_in = depth_dev; P.composite = 1;
+    return dispatch(t, P, false, false, (cudaStream_t)stream_);
+}
+
+int vr_render_surface(const vr_tree* t, const vr_camera* cam, const vr_options* opt, unsigned long long rgba8_surf,
+                      unsigned long long depth_surf, void* stream_) {
+    vr_rect r;
+    int rc = check_common(t, cam, opt, nullptr, r);
+    if (rc) return rc;
+    if (!rgba8_surf) return fail(VR_EINVAL, "null surface");
+    LaunchDev P{};
+    P.tree = t->dev;
+    fill_opt(P.opt, opt);
+    fill_cam(P.cam, cam);
+    P.n_views = 1;
+    P.x0 = 0; P.y0 = 0; P.w = r.w; P.h = r.h;
+    P.surf = (cudaSurfaceObject_t)rgba8_surf; P.dsurf = (cudaSurfaceObject_t)depth_surf;
+    P.composite = depth_surf != 0;
+    return dispatch(t, P, false, true, (cudaStream_t)stream_);
+}
+
+int vr_render_frames_host(const vr_tree* t, const vr_camera* cams, int n_views, const vr_options* opt,
+                          uint8_t* rgba8_host) {
+    if (n_views < 0) return fail(VR_EINVAL, "n_views < 0");
+    if (n_views == 0) return VR_OK;
+    if (!rgba8_host) return fail(VR_EINVAL, "null host buffer");
+    vr_rect r;
+    int rc = check_common(t, cams, opt, nullptr, r);
+    if (rc) return rc;
+    const size_t frame = (size_t)4 * r.w * r.h;
+    constexpr int kRing = 4;
+    struct Res {
+        uint8_t* buf[kRing] = {};
+        cudaEvent_t rendered[kRing] = {}, copied[kRing] = {};
+        cudaStream_t sr = nullptr, sc = nullptr;
+        ~Res() {
+            for (int i = 0; i < kRing; ++i) {
+                cudaFree(buf[i]);
+                if (rendered[i]) cudaEventDestroy(rendered[i]);
+                if (copied[i]) cudaEventDestroy(copied[i]);
+            }
+            if (sr) cudaStreamDestroy(sr);
+            if (sc) cudaStreamDestroy(sc);
+        }
+    } R;
+    VR_CUDA(cudaStreamCreateWithFlags(&R.sr, cudaStreamNonBlocking));
+    VR_CUDA(cudaStreamCreateWithFlags(&R.sc, cudaStreamNonBlocking));
+    for (int i = 0; i < kRing; ++i) {
+        VR_CUDA(cudaMalloc(&R.buf[i], frame));
+        VR_CUDA(cudaEventCreateWithFlags(&R.rendered[i], cudaEventDisableTiming));
+        VR_CUDA(cudaEventCreateWithFlags(&R.copied[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < n_views; ++i) {
+        const int s = i % kRing;
+        if (i >= kRing) VR_CUDA(cudaStreamWaitEvent(R.sr, R.copied[s], 0));
+        rc = vr_render(t, &cams[i], opt, nullptr, R.buf[s], nullptr, nullptr, R.sr);
+        if (rc) return rc;
+        VR_CUDA(cudaEventRecord(R.rendered[s], R.sr));
+        VR_CUDA(cudaStreamWaitEvent(R.sc, R.rendered[s], 0));
+        VR_CUDA(cudaMemcpyAsync(rgba8_host + (size_t)i * frame, R.buf[s], frame, cudaMemcpyDeviceToHost, R.sc));
+        VR_CUDA(cudaEventRecord(R.copied[s], R.sc));
+    }
+    VR_CUDA(cudaStreamSynchronize(R.sc));
+    VR_CUDA(cudaStreamSynchronize(R.sr));
+    return VR_OK;
+}
+
+int vr_probe_lumisphere(const vr_tree* t, const float xyz[3], float* out_dev, void* stream_) {
+    if (!t || !xyz || !out_dev) return fail(VR_EINVAL, "null argument");
+    const int n_out = t->data_dim - 1;
+    if (t->dev.kbd > 0 && t->dev.kbd != t->dev.basis_dim)
+        return fail(VR_EUNSUPPORTED, "probe unavailable for basis_dim %d (only coefficient 0 is resident)", t->dev.basis_dim);
+    probe_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(t->dev, xyz[0], xyz[1], xyz[2], n_out, out_dev);
+    VR_CUDA(cudaGetLastError());
+    g_launches += 1;
+    return VR_OK;
+}
+
+}  // extern "C"

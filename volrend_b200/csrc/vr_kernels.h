@@ -1,0 +1,29 @@
+// vr_kernels.h -- host-side launch interface of the march kernels (one TU per basis size).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "vr_types.h"
+
+namespace vrb {
+
+// variant: 1 tile kernel, 2 tile + TMA top grid, 3 persistent, 4 persistent + TMA top grid
+struct LaunchCfg {
+    int variant;
+    bool count;      // instrumented build: accumulate vr_counters
+    bool surface;    // write a cudaSurfaceObject instead of linear memory
+    int num_sms;
+    unsigned int* queue;  // persistent kernels: {work head, done CTAs}
+    cudaStream_t stream;
+};
+
+template <int KBD>
+cudaError_t launch_march(LaunchDev& P, const LaunchCfg& cfg);
+
+extern template cudaError_t launch_march<-1>(LaunchDev&, const LaunchCfg&);
+extern template cudaError_t launch_march<1>(LaunchDev&, const LaunchCfg&);
+extern template cudaError_t launch_march<4>(LaunchDev&, const LaunchCfg&);
+extern template cudaError_t launch_march<9>(LaunchDev&, const LaunchCfg&);
+extern template cudaError_t launch_march<16>(LaunchDev&, const LaunchCfg&);
+extern template cudaError_t launch_march<25>(LaunchDev&, const LaunchCfg&);
+
+}  // namespace vrb

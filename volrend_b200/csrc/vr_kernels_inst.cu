@@ -1,0 +1,74 @@
+// vr_kernels_inst.cu -- instantiates the march kernels for one basis size (-DVR_KBD=...).
+// Compiled six times (RGBA, SH/SG/ASG 1, 4, 9, 16, 25) so the builds run in parallel.
+#include "vr_kernels.h"
+#include "vr_march.cuh"
+
+#ifndef VR_KBD
+#error "compile with -DVR_KBD=<-1|1|4|9|16|25>"
+#endif
+
+namespace vrb {
+
+namespace {
+
+template <typename K>
+int resident_ctas(K kernel, size_t smem, int num_sms) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    return per_sm * num_sms;
+}
+
+template <int KBD, bool TOP, bool COUNT, int OUT>
+cudaError_t launch_tile(const LaunchDev& P, const LaunchCfg& cfg) {
+    const size_t smem = march_smem_bytes<TOP>(P.tree.max_depth);
+    dim3 grid((P.w + kTileW - 1) / kTileW, (P.h + kTileH - 1) / kTileH, P.n_views);
+    march_tile_kernel<KBD, TOP, COUNT, OUT><<<grid, kBlock, smem, cfg.stream>>>(P);
+    return cudaGetLastError();
+}
+
+template <int KBD, bool TOP, bool COUNT, int OUT>
+cudaError_t launch_persistent(LaunchDev& P, const LaunchCfg& cfg) {
+    const size_t smem = march_smem_bytes<TOP>(P.tree.max_depth);
+    static int cached_ctas = 0, cached_depth = -1;
+    if (cached_ctas == 0 || cached_depth != P.tree.max_depth) {
+        cached_ctas = resident_ctas(march_persistent_kernel<KBD, TOP, COUNT, OUT>, smem, cfg.num_sms);
+        cached_depth = P.tree.max_depth;
+    }
+    P.tiles_x = (P.w + 7) / 8;
+    P.tiles_y = (P.h + 3) / 4;
+    P.n_tiles = P.tiles_x * P.tiles_y * P.n_views;
+    P.work_counter = cfg.queue;
+    int grid = cached_ctas;
+    const int need = (P.n_tiles + (kBlock / 32) - 1) / (kBlock / 32);
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    march_persistent_kernel<KBD, TOP, COUNT, OUT><<<grid, kBlock, smem, cfg.stream>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+template <int KBD>
+cudaError_t launch_march(LaunchDev& P, const LaunchCfg& cfg) {
+    const bool top = (cfg.variant == 2 || cfg.variant == 4);
+    const bool persistent = (cfg.variant >= 3);
+    if (cfg.surface) {  // drop-in launch_renderer path: always the default structure
+        return top ? launch_persistent<KBD, true, false, kOutSurface>(P, cfg)
+                   : launch_persistent<KBD, false, false, kOutSurface>(P, cfg);
+    }
+    if (cfg.count) {
+        return top ? launch_persistent<KBD, true, true, kOutLinear>(P, cfg)
+                   : launch_persistent<KBD, false, true, kOutLinear>(P, cfg);
+    }
+    if (persistent) {
+        return top ? launch_persistent<KBD, true, false, kOutLinear>(P, cfg)
+                   : launch_persistent<KBD, false, false, kOutLinear>(P, cfg);
+    }
+    return top ? launch_tile<KBD, true, false, kOutLinear>(P, cfg)
+               : launch_tile<KBD, false, false, kOutLinear>(P, cfg);
+}
+
+template cudaError_t launch_march<VR_KBD>(LaunchDev&, const LaunchCfg&);
+
+}  // namespace vrb

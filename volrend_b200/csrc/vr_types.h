@@ -1,0 +1,73 @@
+// vr_types.h -- device-side parameter blocks shared by the C-ABI and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "volrend_b200.h"
+
+namespace vrb {
+
+// Leaf flag of a node word; the low 16 bits then hold sigma as fp16 bits.
+constexpr uint32_t kLeafBit = 0x80000000u;
+// Level of the dense top grid staged into shared memory (16^3 cells).
+constexpr int kTopLevel = 4;
+constexpr int kTopCells = 1 << (3 * kTopLevel);
+// Deepest leaf we accept: positions are 24-bit fixed point (fp32 mantissa).
+constexpr int kMaxTreeDepth = 23;
+
+// Device copy of one N3Tree, re-laid-out at upload (vr_tree_create):
+//  nodes[node*8 + oct]  internal: absolute child node id (>0)
+//                       leaf:     kLeafBit | sigma_fp16_bits
+//  recs[(node*8+oct)*rec_bytes ...]  colour coefficients only (sigma moved into the
+//                       node word), channel-major fp16, padded to a 16-byte multiple
+//                       (8 bytes for one coefficient per channel)
+//  top[cell]            16^3 dense grid: (depth<<28)|node of the deepest internal node
+//                       (depth <= kTopLevel-1) on the path to that level-4 cell
+struct TreeDev {
+    const uint32_t* nodes;
+    const unsigned char* recs;
+    const uint32_t* top;
+    const float* extra;
+    float offset[3];
+    float scale[3];
+    float ndc_width, ndc_height, ndc_focal;
+    int32_t N;          // 0: nothing to draw (background only)
+    int32_t format;     // VR_FMT_*
+    int32_t basis_dim;  // reference basis_dim (-1 RGBA)
+    int32_t kbd;        // kernel basis: -1 RGBA, 1, 4, 9, 16, 25 (others collapse to 1)
+    int32_t rec_bytes;
+    int32_t max_depth;
+};
+
+struct CamDev {
+    int32_t width, height;
+    float fx, fy;
+    float c2w[12];
+};
+
+struct OptDev {
+    float step_size, sigma_thresh, stop_thresh, background_brightness;
+    float render_bbox[6];
+    int32_t basis_min, basis_max;
+    float rot_dirs[3];
+    int32_t render_depth;
+};
+
+struct LaunchDev {
+    TreeDev tree;
+    OptDev opt;
+    CamDev cam;            // used when cams == nullptr
+    const CamDev* cams;    // device array for batches
+    int32_t n_views;
+    int32_t x0, y0, w, h;  // tile inside the cam.width x cam.height frame
+    uint8_t* rgba8;        // linear tile-sized RGBA8 per view (or nullptr)
+    float4* rgbaf;         // linear tile-sized float4 per view (or nullptr)
+    const float* depth_in; // composite mode: per-pixel t limit (world units)
+    vr_counters* counters; // device counters (instrumented kernels only)
+    cudaSurfaceObject_t surf, dsurf;
+    int32_t composite;     // 1: read existing colour from rgba8/surf + depth limit
+    int32_t tiles_x, tiles_y, n_tiles;  // persistent kernels: work decomposition
+    unsigned int* work_counter;         // persistent kernels: global tile queue head
+};
+
+}  // namespace vrb
