@@ -16,6 +16,7 @@ from volrend_b200 import synth, N3Tree, Camera, RenderOptions, launch_renderer, 
 from oracle import binding as ob  # noqa: E402
 from oracle import ref_binding as rb  # noqa: E402
 
+VARIANTS = [int(v) for v in os.environ.get("VR_VARIANTS", "1,3,5,6").split(",")]
 out = {}
 os.makedirs("gpurun_out", exist_ok=True)
 dev = torch.device("cuda:0")
@@ -52,7 +53,7 @@ def parity(name, st, W, H, pose, **optkw):
         q[..., :3] = np.floor(np.clip(f_r[..., :3] * np.float32(255.0), 0, None)).astype(np.uint32) & 0xff
         q[..., 3] = 255
         res["reftap_vs_refu8"] = cmp(q, u_r)
-    for variant in (1, 2, 3, 4):
+    for variant in VARIANTS:
         lib().vr_set_variant(variant)
         img = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
         fo = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
@@ -110,9 +111,9 @@ cn = cnt.cpu().numpy().tolist()
 timing["counters_200"] = cn
 A = 4 * cn[1] + 2 * cn[0] + 6 * 16 * cn[2] + 4 * W * H * len(cams)
 timing["A_bytes_per_frame"] = A / len(cams)
-for variant in (1, 2, 3, 4):
+for variant in VARIANTS:
     lib().vr_set_variant(variant)
-    for mode in ("loop", "batch"):
+    for mode in ("batch",):
         for rep in range(3):
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -26,7 +26,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<int> g_variant{0};
 std::atomic<unsigned long long> g_launches{0};
-constexpr int kDefaultVariant = 4;
+constexpr int kDefaultVariant = 5;
 constexpr int kQueueSlots = 256;
 
 int fail(int code, const char* fmt, ...) {
@@ -187,7 +187,7 @@ extern "C" {
 const char* vr_last_error(void) { return g_err.c_str(); }
 const char* vr_version(void) { return "volrend_b200 0.1 (sm_100a)"; }
 int vr_set_variant(int variant) {
-    if (variant < 0 || variant > 4) return fail(VR_EINVAL, "variant must be 0..4");
+    if (variant < 0 || (variant & 15) > 6 || variant > 255) return fail(VR_EINVAL, "variant must be kind 0..6 (+16*tune)");
     g_variant.store(variant);
     return VR_OK;
 }

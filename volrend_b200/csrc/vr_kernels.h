@@ -6,7 +6,8 @@
 
 namespace vrb {
 
-// variant: 1 tile kernel, 2 tile + TMA top grid, 3 persistent, 4 persistent + TMA top grid
+// variant: 1 tile kernel, 2 tile + TMA top grid, 3 persistent, 4 persistent + TMA top grid,
+//          5 persistent + deferred shading, 6 same + TMA top grid
 struct LaunchCfg {
     int variant;
     bool count;      // instrumented build: accumulate vr_counters

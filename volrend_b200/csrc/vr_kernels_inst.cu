@@ -27,12 +27,12 @@ cudaError_t launch_tile(const LaunchDev& P, const LaunchCfg& cfg) {
     return cudaGetLastError();
 }
 
-template <int KBD, bool TOP, bool COUNT, int OUT>
+template <int KBD, bool TOP, bool COUNT, int OUT, int TUNE = 0>
 cudaError_t launch_persistent(LaunchDev& P, const LaunchCfg& cfg) {
     const size_t smem = march_smem_bytes<TOP>(P.tree.max_depth);
     static int cached_ctas = 0, cached_depth = -1;
     if (cached_ctas == 0 || cached_depth != P.tree.max_depth) {
-        cached_ctas = resident_ctas(march_persistent_kernel<KBD, TOP, COUNT, OUT>, smem, cfg.num_sms);
+        cached_ctas = resident_ctas(march_persistent_kernel<KBD, TOP, COUNT, OUT, TUNE>, smem, cfg.num_sms);
         cached_depth = P.tree.max_depth;
     }
     P.tiles_x = (P.w + 7) / 8;
@@ -43,7 +43,27 @@ cudaError_t launch_persistent(LaunchDev& P, const LaunchCfg& cfg) {
     const int need = (P.n_tiles + (kBlock / 32) - 1) / (kBlock / 32);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    march_persistent_kernel<KBD, TOP, COUNT, OUT><<<grid, kBlock, smem, cfg.stream>>>(P);
+    march_persistent_kernel<KBD, TOP, COUNT, OUT, TUNE><<<grid, kBlock, smem, cfg.stream>>>(P);
+    return cudaGetLastError();
+}
+
+template <int KBD, bool TOP, bool COUNT, int OUT>
+cudaError_t launch_deferred(LaunchDev& P, const LaunchCfg& cfg) {
+    const size_t smem = deferred_smem_bytes<TOP>(P.tree.max_depth);
+    static int cached_ctas = 0, cached_depth = -1;
+    if (cached_ctas == 0 || cached_depth != P.tree.max_depth) {
+        cached_ctas = resident_ctas(march_deferred_kernel<KBD, TOP, COUNT, OUT>, smem, cfg.num_sms);
+        cached_depth = P.tree.max_depth;
+    }
+    P.tiles_x = (P.w + 7) / 8;
+    P.tiles_y = (P.h + 3) / 4;
+    P.n_tiles = P.tiles_x * P.tiles_y * P.n_views;
+    P.work_counter = cfg.queue;
+    int grid = cached_ctas;
+    const int need = (P.n_tiles + (kBlock / 32) - 1) / (kBlock / 32);
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    march_deferred_kernel<KBD, TOP, COUNT, OUT><<<grid, kBlock, smem, cfg.stream>>>(P);
     return cudaGetLastError();
 }
 
@@ -51,15 +71,31 @@ cudaError_t launch_persistent(LaunchDev& P, const LaunchCfg& cfg) {
 
 template <int KBD>
 cudaError_t launch_march(LaunchDev& P, const LaunchCfg& cfg) {
-    const bool top = (cfg.variant == 2 || cfg.variant == 4);
-    const bool persistent = (cfg.variant >= 3);
-    if (cfg.surface) {  // drop-in launch_renderer path: always the default structure
-        return top ? launch_persistent<KBD, true, false, kOutSurface>(P, cfg)
-                   : launch_persistent<KBD, false, false, kOutSurface>(P, cfg);
+    const int kind = cfg.variant & 15, tune = cfg.variant >> 4;
+    const bool top = (kind == 2 || kind == 4 || kind == 6);
+    const bool persistent = (kind == 3 || kind == 4);
+    const bool deferred = kind >= 5;
+    if (kind == 3 && tune && !cfg.surface && !cfg.count) {  // measurement knobs on the persistent kernel
+        switch (tune) {
+            case 1: return launch_persistent<KBD, false, false, kOutLinear, 1>(P, cfg);
+            case 2: return launch_persistent<KBD, false, false, kOutLinear, 2>(P, cfg);
+            case 3: return launch_persistent<KBD, false, false, kOutLinear, 3>(P, cfg);
+            case 8: return launch_persistent<KBD, false, false, kOutLinear, 8>(P, cfg);
+            case 10: return launch_persistent<KBD, false, false, kOutLinear, 10>(P, cfg);
+            default: return cudaErrorInvalidValue;
+        }
     }
-    if (cfg.count) {
-        return top ? launch_persistent<KBD, true, true, kOutLinear>(P, cfg)
-                   : launch_persistent<KBD, false, true, kOutLinear>(P, cfg);
+    if (cfg.surface) {  // drop-in launch_renderer path
+        return top ? launch_deferred<KBD, true, false, kOutSurface>(P, cfg)
+                   : launch_deferred<KBD, false, false, kOutSurface>(P, cfg);
+    }
+    if (cfg.count) {  // instrumented build
+        return top ? launch_deferred<KBD, true, true, kOutLinear>(P, cfg)
+                   : launch_deferred<KBD, false, true, kOutLinear>(P, cfg);
+    }
+    if (deferred) {
+        return top ? launch_deferred<KBD, true, false, kOutLinear>(P, cfg)
+                   : launch_deferred<KBD, false, false, kOutLinear>(P, cfg);
     }
     if (persistent) {
         return top ? launch_persistent<KBD, true, false, kOutLinear>(P, cfg)
