@@ -26,7 +26,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<int> g_variant{0};
 std::atomic<unsigned long long> g_launches{0};
-constexpr int kDefaultVariant = 5;
+constexpr int kDefaultVariant = 19;  // persistent warps + cache-policy hints (kind 3, tune 1)
 constexpr int kQueueSlots = 256;
 
 int fail(int code, const char* fmt, ...) {
@@ -455,47 +455,62 @@ int vr_render_surface(const vr_tree* t, const vr_camera* cam, const vr_options* 
 
 int vr_render_frames_host(const vr_tree* t, const vr_camera* cams, int n_views, const vr_options* opt,
                           uint8_t* rgba8_host) {
+    // main_headless.cpp:208-223 with -o: every frame goes back to host memory.  Frames are
+    // rendered in chunks of a few views per launch on two alternating streams (the tail of
+    // one chunk overlaps the head of the next) and copied out on a third stream while the
+    // following chunks render.
     if (n_views < 0) return fail(VR_EINVAL, "n_views < 0");
     if (n_views == 0) return VR_OK;
     if (!rgba8_host) return fail(VR_EINVAL, "null host buffer");
     vr_rect r;
     int rc = check_common(t, cams, opt, nullptr, r);
     if (rc) return rc;
+    for (int i = 1; i < n_views; ++i)
+        if (cams[i].width != cams[0].width || cams[i].height != cams[0].height)
+            return fail(VR_EINVAL, "all views must share one image size");
     const size_t frame = (size_t)4 * r.w * r.h;
+    int chunk = 8;
+    if (const char* e = getenv("VR_HOST_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
+    if (chunk > n_views) chunk = n_views;
     constexpr int kRing = 4;
     struct Res {
         uint8_t* buf[kRing] = {};
         cudaEvent_t rendered[kRing] = {}, copied[kRing] = {};
-        cudaStream_t sr = nullptr, sc = nullptr;
+        cudaStream_t sr[2] = {nullptr, nullptr}, sc = nullptr;
         ~Res() {
             for (int i = 0; i < kRing; ++i) {
                 cudaFree(buf[i]);
                 if (rendered[i]) cudaEventDestroy(rendered[i]);
                 if (copied[i]) cudaEventDestroy(copied[i]);
             }
-            if (sr) cudaStreamDestroy(sr);
+            for (auto s : sr) if (s) cudaStreamDestroy(s);
             if (sc) cudaStreamDestroy(sc);
         }
     } R;
-    VR_CUDA(cudaStreamCreateWithFlags(&R.sr, cudaStreamNonBlocking));
+    VR_CUDA(cudaStreamCreateWithFlags(&R.sr[0], cudaStreamNonBlocking));
+    VR_CUDA(cudaStreamCreateWithFlags(&R.sr[1], cudaStreamNonBlocking));
     VR_CUDA(cudaStreamCreateWithFlags(&R.sc, cudaStreamNonBlocking));
     for (int i = 0; i < kRing; ++i) {
-        VR_CUDA(cudaMalloc(&R.buf[i], frame));
+        VR_CUDA(cudaMalloc(&R.buf[i], frame * chunk));
         VR_CUDA(cudaEventCreateWithFlags(&R.rendered[i], cudaEventDisableTiming));
         VR_CUDA(cudaEventCreateWithFlags(&R.copied[i], cudaEventDisableTiming));
     }
-    for (int i = 0; i < n_views; ++i) {
-        const int s = i % kRing;
-        if (i >= kRing) VR_CUDA(cudaStreamWaitEvent(R.sr, R.copied[s], 0));
-        rc = vr_render(t, &cams[i], opt, nullptr, R.buf[s], nullptr, nullptr, R.sr);
+    int c = 0;
+    for (int v0 = 0; v0 < n_views; v0 += chunk, ++c) {
+        const int nv = n_views - v0 < chunk ? n_views - v0 : chunk;
+        const int s = c % kRing;
+        cudaStream_t sr = R.sr[c & 1];
+        if (c >= kRing) VR_CUDA(cudaStreamWaitEvent(sr, R.copied[s], 0));
+        rc = vr_render_batch(t, cams + v0, nv, opt, nullptr, R.buf[s], nullptr, nullptr, sr);
         if (rc) return rc;
-        VR_CUDA(cudaEventRecord(R.rendered[s], R.sr));
+        VR_CUDA(cudaEventRecord(R.rendered[s], sr));
         VR_CUDA(cudaStreamWaitEvent(R.sc, R.rendered[s], 0));
-        VR_CUDA(cudaMemcpyAsync(rgba8_host + (size_t)i * frame, R.buf[s], frame, cudaMemcpyDeviceToHost, R.sc));
+        VR_CUDA(cudaMemcpyAsync(rgba8_host + (size_t)v0 * frame, R.buf[s], frame * nv, cudaMemcpyDeviceToHost, R.sc));
         VR_CUDA(cudaEventRecord(R.copied[s], R.sc));
     }
     VR_CUDA(cudaStreamSynchronize(R.sc));
-    VR_CUDA(cudaStreamSynchronize(R.sr));
+    VR_CUDA(cudaStreamSynchronize(R.sr[0]));
+    VR_CUDA(cudaStreamSynchronize(R.sr[1]));
     return VR_OK;
 }
 

@@ -85,13 +85,11 @@ cudaError_t launch_march(LaunchDev& P, const LaunchCfg& cfg) {
             default: return cudaErrorInvalidValue;
         }
     }
-    if (cfg.surface) {  // drop-in launch_renderer path
-        return top ? launch_deferred<KBD, true, false, kOutSurface>(P, cfg)
-                   : launch_deferred<KBD, false, false, kOutSurface>(P, cfg);
+    if (cfg.surface) {  // drop-in launch_renderer path: default kernel writing the caller's cudaArray
+        return launch_persistent<KBD, false, false, kOutSurface, 1>(P, cfg);
     }
-    if (cfg.count) {  // instrumented build
-        return top ? launch_deferred<KBD, true, true, kOutLinear>(P, cfg)
-                   : launch_deferred<KBD, false, true, kOutLinear>(P, cfg);
+    if (cfg.count) {  // instrumented build of the default kernel
+        return launch_persistent<KBD, false, true, kOutLinear, 1>(P, cfg);
     }
     if (deferred) {
         return top ? launch_deferred<KBD, true, false, kOutLinear>(P, cfg)
