@@ -135,6 +135,12 @@ int vr_render_frames_host(const vr_tree* tree, const vr_camera* cams, int n_view
  * out_dev as floats (retrieve_cursor_lumisphere_kernel). */
 int vr_probe_lumisphere(const vr_tree* tree, const float xyz_world[3], float* out_dev, void* stream);
 
+/* Diagnostics: one full-frame render with the instrumented kernel that also records, per 8x4-pixel
+ * work item (row-major tiles of 8x4), {start ns, end ns, SM id, global warp id} into
+ * trace_dev[4 * n_items] (n_items = ceil(w/8)*ceil(h/4)). */
+int vr_debug_trace(const vr_tree* tree, const vr_camera* cam, const vr_options* opt, uint8_t* rgba8_dev,
+                   vr_counters* counters_dev, unsigned long long* trace_dev, void* stream);
+
 /* Kernel variant selection for measurement (0 = default/best). */
 int vr_set_variant(int variant);
 int vr_get_variant(void);

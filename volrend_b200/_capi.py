@@ -67,6 +67,8 @@ SYMBOLS = {
     "vr_render_frames_host": (C.c_int, [C.c_void_p, C.POINTER(vr_camera), C.c_int, C.POINTER(vr_options),
                                         C.c_void_p]),
     "vr_probe_lumisphere": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
+    "vr_debug_trace": (C.c_int, [C.c_void_p, C.POINTER(vr_camera), C.POINTER(vr_options), C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
     "vr_set_variant": (C.c_int, [C.c_int]),
     "vr_get_variant": (C.c_int, []),
     "vr_launch_count": (C.c_ulonglong, []),

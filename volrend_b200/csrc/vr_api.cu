@@ -68,6 +68,7 @@ struct vr_tree {
     std::atomic<unsigned int> next_queue{0};
     vr_tree_info info{};
     int data_dim = 0;
+    size_t l2_window_bytes = 0;  // node-table window kept in persisting L2 (VR_L2_PERSIST=1)
 };
 
 // ------------------------------------------------------------------------------------ re-layout kernels
@@ -187,7 +188,7 @@ extern "C" {
 const char* vr_last_error(void) { return g_err.c_str(); }
 const char* vr_version(void) { return "volrend_b200 0.1 (sm_100a)"; }
 int vr_set_variant(int variant) {
-    if (variant < 0 || (variant & 15) > 6 || variant > 255) return fail(VR_EINVAL, "variant must be kind 0..6 (+16*tune)");
+    if (variant < 0 || (variant & 15) > 6 || variant > 4095) return fail(VR_EINVAL, "variant must be kind 0..6 (+16*tune)");
     g_variant.store(variant);
     return VR_OK;
 }
@@ -309,6 +310,19 @@ int vr_tree_create(const vr_tree_desc* d, vr_tree** out) {
     t->info.capacity = d->capacity; t->info.max_depth = D.max_depth; t->info.rec_bytes = rec_bytes;
     t->info.node_bytes = n_slots * 4; t->info.rec_total_bytes = n_slots * (long long)rec_bytes;
     t->info.top_bytes = kTopCells * 4;
+    if (const char* e = getenv("VR_L2_PERSIST")) {
+        if (atoi(e) > 0) {
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, t->device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, t->device);
+            size_t want = (size_t)n_slots * 4;
+            if (want > (size_t)max_window) want = (size_t)max_window;
+            size_t carve = want < (size_t)max_persist ? want : (size_t)max_persist;
+            if (carve > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess)
+                t->l2_window_bytes = want;
+            cudaGetLastError();
+        }
+    }
     guard.ok = true;
     *out = t;
     return VR_OK;
@@ -344,6 +358,8 @@ int dispatch(const vr_tree* t, LaunchDev& P, bool count, bool surface, cudaStrea
     cfg.count = count; cfg.surface = surface; cfg.num_sms = t->num_sms; cfg.stream = stream;
     vr_tree* mt = const_cast<vr_tree*>(t);
     cfg.queue = mt->queues + 2 * (mt->next_queue.fetch_add(1) % kQueueSlots);
+    cfg.l2_window = t->nodes;
+    cfg.l2_window_bytes = t->l2_window_bytes;
     cudaError_t e;
     switch (t->dev.kbd) {
         case -1: e = launch_march<-1>(P, cfg); break;
@@ -411,6 +427,22 @@ int vr_render_batch(const vr_tree* t, const vr_camera* cams, int n_views, const 
     rc = dispatch(t, P, counters_dev != nullptr, false, stream);
     if (dcams) cudaFreeAsync(dcams, stream);
     return rc;
+}
+
+int vr_debug_trace(const vr_tree* t, const vr_camera* cam, const vr_options* opt, uint8_t* rgba8_dev,
+                   vr_counters* counters_dev, unsigned long long* trace_dev, void* stream_) {
+    vr_rect r;
+    int rc = check_common(t, cam, opt, nullptr, r);
+    if (rc) return rc;
+    if (!counters_dev || !trace_dev) return fail(VR_EINVAL, "trace needs counters and a trace buffer");
+    LaunchDev P{};
+    P.tree = t->dev;
+    fill_opt(P.opt, opt);
+    fill_cam(P.cam, cam);
+    P.n_views = 1;
+    P.x0 = 0; P.y0 = 0; P.w = r.w; P.h = r.h;
+    P.rgba8 = rgba8_dev; P.counters = counters_dev; P.trace = trace_dev;
+    return dispatch(t, P, true, false, (cudaStream_t)stream_);
 }
 
 int vr_render(const vr_tree* t, const vr_camera* cam, const vr_options* opt, const vr_rect* tile, uint8_t* rgba8_dev,

@@ -14,6 +14,8 @@ struct LaunchCfg {
     bool surface;    // write a cudaSurfaceObject instead of linear memory
     int num_sms;
     unsigned int* queue;  // persistent kernels: {work head, done CTAs}
+    const void* l2_window;   // optional persisting-L2 access window (the node table)
+    size_t l2_window_bytes;  // 0 = none
     cudaStream_t stream;
 };
 

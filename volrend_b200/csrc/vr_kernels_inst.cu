@@ -43,6 +43,20 @@ cudaError_t launch_persistent(LaunchDev& P, const LaunchCfg& cfg) {
     const int need = (P.n_tiles + (kBlock / 32) - 1) / (kBlock / 32);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    if (cfg.l2_window_bytes) {
+        // keep the node table resident in the persisting part of L2 across frames
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(grid); lc.blockDim = dim3(kBlock); lc.dynamicSmemBytes = smem; lc.stream = cfg.stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(cfg.l2_window);
+        attr[0].val.accessPolicyWindow.num_bytes = cfg.l2_window_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        lc.attrs = attr; lc.numAttrs = 1;
+        return cudaLaunchKernelEx(&lc, march_persistent_kernel<KBD, TOP, COUNT, OUT, TUNE>, P);
+    }
     march_persistent_kernel<KBD, TOP, COUNT, OUT, TUNE><<<grid, kBlock, smem, cfg.stream>>>(P);
     return cudaGetLastError();
 }
@@ -82,6 +96,8 @@ cudaError_t launch_march(LaunchDev& P, const LaunchCfg& cfg) {
             case 3: return launch_persistent<KBD, false, false, kOutLinear, 3>(P, cfg);
             case 8: return launch_persistent<KBD, false, false, kOutLinear, 8>(P, cfg);
             case 10: return launch_persistent<KBD, false, false, kOutLinear, 10>(P, cfg);
+            case 17: return launch_persistent<KBD, false, false, kOutLinear, 17>(P, cfg);
+            case 16: return launch_persistent<KBD, false, false, kOutLinear, 16>(P, cfg);
             default: return cudaErrorInvalidValue;
         }
     }

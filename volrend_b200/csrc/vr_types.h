@@ -68,6 +68,7 @@ struct LaunchDev {
     int32_t composite;     // 1: read existing colour from rgba8/surf + depth limit
     int32_t tiles_x, tiles_y, n_tiles;  // persistent kernels: work decomposition
     unsigned int* work_counter;         // persistent kernels: global tile queue head
+    unsigned long long* trace;          // diagnostics: per work item {start ns, end ns, smid, warp}
 };
 
 }  // namespace vrb
