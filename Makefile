@@ -10,9 +10,15 @@ CC        ?= gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude -Ivolrend_b200/csrc \
              -diag-suppress 20012
+# tuning builds: make lib VR_BLOCK=128 VR_MINB=7 SUFFIX=_b128m7  (selected at run time with VR_LIB_SUFFIX)
+VR_BLOCK  ?= 128
+VR_MINB   ?= 7
+SUFFIX    ?=
+NVFLAGS   += -DVR_BLOCK=$(VR_BLOCK) -DVR_MINB=$(VR_MINB)
+OBJ       := build/obj$(SUFFIX)
 KBDS      := m1 1 4 9 16 25
-KOBJS     := $(foreach k,$(KBDS),build/obj/vr_kernels_$(k).o)
-LIB       := volrend_b200/libvolrend_b200.so
+KOBJS     := $(foreach k,$(KBDS),$(OBJ)/vr_kernels_$(k).o)
+LIB       := volrend_b200/libvolrend_b200$(SUFFIX).so
 VOLREND_REF ?= /root/reference
 
 .PHONY: all lib oracle ref shim clean
@@ -20,19 +26,19 @@ all: lib oracle
 
 lib: $(LIB)
 
-build/obj/vr_kernels_m1.o: volrend_b200/csrc/vr_kernels_inst.cu volrend_b200/csrc/vr_march.cuh volrend_b200/csrc/vr_types.h volrend_b200/csrc/vr_kernels.h include/volrend_b200.h
-	@mkdir -p build/obj
-	$(NVCC) $(NVFLAGS) -DVR_KBD=-1 -Xptxas -v -c $< -o $@ 2> build/obj/ptxas_m1.log || (cat build/obj/ptxas_m1.log; false)
+$(OBJ)/vr_kernels_m1.o: volrend_b200/csrc/vr_kernels_inst.cu volrend_b200/csrc/vr_march.cuh volrend_b200/csrc/vr_types.h volrend_b200/csrc/vr_kernels.h include/volrend_b200.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -DVR_KBD=-1 -Xptxas -v -c $< -o $@ 2> $(OBJ)/ptxas_m1.log || (cat $(OBJ)/ptxas_m1.log; false)
 
-build/obj/vr_kernels_%.o: volrend_b200/csrc/vr_kernels_inst.cu volrend_b200/csrc/vr_march.cuh volrend_b200/csrc/vr_types.h volrend_b200/csrc/vr_kernels.h include/volrend_b200.h
-	@mkdir -p build/obj
-	$(NVCC) $(NVFLAGS) -DVR_KBD=$* -Xptxas -v -c $< -o $@ 2> build/obj/ptxas_$*.log || (cat build/obj/ptxas_$*.log; false)
+$(OBJ)/vr_kernels_%.o: volrend_b200/csrc/vr_kernels_inst.cu volrend_b200/csrc/vr_march.cuh volrend_b200/csrc/vr_types.h volrend_b200/csrc/vr_kernels.h include/volrend_b200.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -DVR_KBD=$* -Xptxas -v -c $< -o $@ 2> $(OBJ)/ptxas_$*.log || (cat $(OBJ)/ptxas_$*.log; false)
 
-build/obj/vr_api.o: volrend_b200/csrc/vr_api.cu volrend_b200/csrc/vr_types.h volrend_b200/csrc/vr_kernels.h include/volrend_b200.h
-	@mkdir -p build/obj
+$(OBJ)/vr_api.o: volrend_b200/csrc/vr_api.cu volrend_b200/csrc/vr_types.h volrend_b200/csrc/vr_kernels.h include/volrend_b200.h
+	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
-$(LIB): build/obj/vr_api.o $(KOBJS)
+$(LIB): $(OBJ)/vr_api.o $(KOBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $^
 
 oracle: oracle/liboracle.so

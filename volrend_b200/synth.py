@@ -105,6 +105,18 @@ def sdf_gyroid(p):
     return np.maximum(d, ball)
 
 
+def sdf_gyroid_small(p):
+    """Config 4 (depth 11): the same gyroid sheet clipped to a small ball, so that a 2048^3
+    refinement stays around a million nodes."""
+    w = 2.0 * math.pi * 4.0
+    q = p * np.float32(w)
+    g = (np.sin(q[..., 0]) * np.cos(q[..., 1]) + np.sin(q[..., 1]) * np.cos(q[..., 2])
+         + np.sin(q[..., 2]) * np.cos(q[..., 0]))
+    d = np.abs(g) / np.float32(w * 1.5)
+    ball = _sd_sphere(p, (0.5, 0.5, 0.5), 0.17)
+    return np.maximum(d, ball)
+
+
 def _scaled(fn, s):
     """Shrink a shape about the cube centre by 1/s (keeps distances metric)."""
     def g(p):
@@ -113,7 +125,7 @@ def _scaled(fn, s):
 
 
 SDFS = {"shell": sdf_shell, "lego": _scaled(sdf_lego, 1.25), "drums": _scaled(sdf_drums, 1.35),
-        "gyroid": sdf_gyroid}
+        "gyroid": sdf_gyroid, "gyroid_small": sdf_gyroid_small}
 
 
 # ----------------------------------------------------------------------------------------
