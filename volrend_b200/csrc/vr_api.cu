@@ -28,6 +28,7 @@ std::atomic<int> g_variant{0};
 std::atomic<unsigned long long> g_launches{0};
 constexpr int kDefaultVariant = 19;  // persistent warps + cache-policy hints (kind 3, tune 1)
 constexpr int kQueueSlots = 256;
+constexpr int kCamRing = 8192;  // device ring of per-view cameras for batched launches
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -65,6 +66,9 @@ struct vr_tree {
     uint32_t* top = nullptr;
     float* extra = nullptr;
     unsigned int* queues = nullptr;  // kQueueSlots x {head, done}
+    CamDev* cam_ring = nullptr;      // kCamRing entries; batches take consecutive slots
+    std::mutex cam_mu;
+    unsigned int cam_pos = 0;
     std::atomic<unsigned int> next_queue{0};
     vr_tree_info info{};
     int data_dim = 0;
@@ -213,6 +217,7 @@ void vr_tree_destroy(vr_tree* t) {
     cudaGetDevice(&prev);
     cudaSetDevice(t->device);
     cudaFree(t->nodes); cudaFree(t->recs); cudaFree(t->top); cudaFree(t->extra); cudaFree(t->queues);
+    cudaFree(t->cam_ring);
     cudaSetDevice(prev);
     delete t;
 }
@@ -262,6 +267,7 @@ int vr_tree_create(const vr_tree_desc* d, vr_tree** out) {
     VR_CUDA(cudaMalloc(&t->top, kTopCells * 4));
     VR_CUDA(cudaMalloc(&t->queues, kQueueSlots * 2 * sizeof(unsigned int)));
     VR_CUDA(cudaMemset(t->queues, 0, kQueueSlots * 2 * sizeof(unsigned int)));
+    VR_CUDA(cudaMalloc(&t->cam_ring, kCamRing * sizeof(CamDev)));
     VR_CUDA(cudaMemcpy(raw_child, d->child, child_bytes, cudaMemcpyHostToDevice));
     VR_CUDA(cudaMemcpy(raw_data, d->data, data_bytes, cudaMemcpyHostToDevice));
     VR_CUDA(cudaMemset(flags, 0, 2 * sizeof(int)));
@@ -415,18 +421,35 @@ int vr_render_batch(const vr_tree* t, const vr_camera* cams, int n_views, const 
     P.x0 = r.x0; P.y0 = r.y0; P.w = r.w; P.h = r.h;
     P.rgba8 = rgba8_dev; P.rgbaf = reinterpret_cast<float4*>(rgba32f_dev);
     P.counters = counters_dev;
-    CamDev* dcams = nullptr;
+    if (n_views > kCamRing) {  // split very large batches so each fits the camera ring
+        const size_t tile_px = (size_t)r.w * r.h;
+        for (int v0 = 0; v0 < n_views; v0 += kCamRing) {
+            const int nv = n_views - v0 < kCamRing ? n_views - v0 : kCamRing;
+            rc = vr_render_batch(t, cams + v0, nv, opt, tile, rgba8_dev ? rgba8_dev + 4 * tile_px * v0 : nullptr,
+                                 rgba32f_dev ? rgba32f_dev + 4 * tile_px * v0 : nullptr, counters_dev, stream_);
+            if (rc) return rc;
+        }
+        return VR_OK;
+    }
     if (n_views > 1) {
+        // cameras go through a device ring owned by the tree (no allocation on the launch path: a
+        // stream-ordered pool would hand memory back to the OS at every synchronisation)
+        vr_tree* mt = const_cast<vr_tree*>(t);
+        unsigned int slot;
+        {
+            std::lock_guard<std::mutex> lk(mt->cam_mu);
+            if (mt->cam_pos + (unsigned int)n_views > (unsigned int)kCamRing) mt->cam_pos = 0;  // no wrap inside a batch
+            slot = mt->cam_pos;
+            mt->cam_pos += (unsigned int)n_views;
+        }
         std::vector<CamDev> h(n_views);
         for (int i = 0; i < n_views; ++i) fill_cam(h[i], &cams[i]);
-        VR_CUDA(cudaMallocAsync(&dcams, sizeof(CamDev) * n_views, stream));
+        CamDev* dcams = mt->cam_ring + slot;
         VR_CUDA(cudaMemcpyAsync(dcams, h.data(), sizeof(CamDev) * n_views, cudaMemcpyHostToDevice, stream));
         // pageable source: the copy has been staged when cudaMemcpyAsync returns
         P.cams = dcams;
     }
-    rc = dispatch(t, P, counters_dev != nullptr, false, stream);
-    if (dcams) cudaFreeAsync(dcams, stream);
-    return rc;
+    return dispatch(t, P, counters_dev != nullptr, false, stream);
 }
 
 int vr_debug_trace(const vr_tree* t, const vr_camera* cam, const vr_options* opt, uint8_t* rgba8_dev,
