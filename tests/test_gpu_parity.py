@@ -342,3 +342,34 @@ def test_cxx_shim_and_headless_cli(built, small_trees, tmp_path):
     r = subprocess.run([cli, path, "-w", "80", "-h", "60", "--fx", str(synth.focal_for(80))] + ppaths,
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ms per frame" in r.stdout and "fps" in r.stdout
+
+
+def test_back_to_back_launches_keep_stream_order(built, dev_trees):
+    """Per-frame launches overlap their predecessor's tail (programmatic dependent launch);
+    stream order must still hold: same-buffer launches leave the LAST frame, separate buffers
+    each hold their own frame, and a composite launch sees the image its predecessor wrote."""
+    torch = _torch()
+    from volrend_b200 import RenderOptions, launch_renderer, synth
+    st, tree = dev_trees["sh16_d6"]
+    cams = [make_cam(200, 160, p) for p in synth.nerf_synthetic_test_poses(12)]
+    opt = RenderOptions()
+    solo = [gpu_render(tree, c, opt)[1] for c in cams]
+    same = torch.zeros((160, 200, 4), dtype=torch.uint8, device="cuda")
+    sep = torch.zeros((len(cams), 160, 200, 4), dtype=torch.uint8, device="cuda")
+    for rep in range(3):
+        for i, c in enumerate(cams):
+            launch_renderer(tree, c, opt, same, None, None, True)
+        for i, c in enumerate(cams):
+            launch_renderer(tree, c, opt, sep[i], None, None, True)
+        torch.cuda.synchronize()
+        assert np.array_equal(same.cpu().numpy(), solo[-1])
+        for i in range(len(cams)):
+            assert np.array_equal(sep[i].cpu().numpy(), solo[i]), i
+    # offscreen render followed immediately by a composite pass over it (reads what was just written)
+    img = torch.zeros((160, 200, 4), dtype=torch.uint8, device="cuda")
+    depth = torch.full((160, 200), 1e9, dtype=torch.float32, device="cuda")
+    launch_renderer(tree, cams[0], opt, img, None, None, True)
+    launch_renderer(tree, cams[1], opt, img, depth, None, False)
+    torch.cuda.synchronize()
+    _, want, _ = oracle_render(st, cams[1], {}, rgba_in=solo[0], depth_in=np.full((160, 200), 1e9, np.float32))
+    assert (img.cpu().numpy() != want).any(-1).sum() <= 2

@@ -69,6 +69,16 @@ struct vr_tree {
     CamDev* cam_ring = nullptr;      // kCamRing entries; batches take consecutive slots
     std::mutex cam_mu;
     unsigned int cam_pos = 0;
+    // vr_render_frames_host: chunk ring, streams and events are created once and kept
+    struct HostPath {
+        static constexpr int kRing = 4;
+        uint8_t* buf[kRing] = {};
+        size_t buf_bytes = 0;
+        cudaEvent_t rendered[kRing] = {}, copied[kRing] = {};
+        cudaStream_t sr[2] = {nullptr, nullptr}, sc = nullptr;
+        bool ready = false;
+    } host;
+    std::mutex host_mu;
     std::atomic<unsigned int> next_queue{0};
     vr_tree_info info{};
     int data_dim = 0;
@@ -218,6 +228,13 @@ void vr_tree_destroy(vr_tree* t) {
     cudaSetDevice(t->device);
     cudaFree(t->nodes); cudaFree(t->recs); cudaFree(t->top); cudaFree(t->extra); cudaFree(t->queues);
     cudaFree(t->cam_ring);
+    for (int i = 0; i < vr_tree::HostPath::kRing; ++i) {
+        cudaFree(t->host.buf[i]);
+        if (t->host.rendered[i]) cudaEventDestroy(t->host.rendered[i]);
+        if (t->host.copied[i]) cudaEventDestroy(t->host.copied[i]);
+    }
+    for (auto st : t->host.sr) if (st) cudaStreamDestroy(st);
+    if (t->host.sc) cudaStreamDestroy(t->host.sc);
     cudaSetDevice(prev);
     delete t;
 }
@@ -366,6 +383,8 @@ int dispatch(const vr_tree* t, LaunchDev& P, bool count, bool surface, cudaStrea
     cfg.queue = mt->queues + 2 * (mt->next_queue.fetch_add(1) % kQueueSlots);
     cfg.l2_window = t->nodes;
     cfg.l2_window_bytes = t->l2_window_bytes;
+    static const bool no_pdl = getenv("VR_NO_PDL") != nullptr && atoi(getenv("VR_NO_PDL")) > 0;
+    cfg.pdl = !no_pdl;
     cudaError_t e;
     switch (t->dev.kbd) {
         case -1: e = launch_march<-1>(P, cfg); break;
@@ -527,28 +546,25 @@ int vr_render_frames_host(const vr_tree* t, const vr_camera* cams, int n_views, 
     int chunk = 8;
     if (const char* e = getenv("VR_HOST_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
     if (chunk > n_views) chunk = n_views;
-    constexpr int kRing = 4;
-    struct Res {
-        uint8_t* buf[kRing] = {};
-        cudaEvent_t rendered[kRing] = {}, copied[kRing] = {};
-        cudaStream_t sr[2] = {nullptr, nullptr}, sc = nullptr;
-        ~Res() {
-            for (int i = 0; i < kRing; ++i) {
-                cudaFree(buf[i]);
-                if (rendered[i]) cudaEventDestroy(rendered[i]);
-                if (copied[i]) cudaEventDestroy(copied[i]);
-            }
-            for (auto s : sr) if (s) cudaStreamDestroy(s);
-            if (sc) cudaStreamDestroy(sc);
+    vr_tree* mt = const_cast<vr_tree*>(t);
+    std::lock_guard<std::mutex> host_lock(mt->host_mu);   // one host-path sweep per tree at a time
+    vr_tree::HostPath& R = mt->host;
+    constexpr int kRing = vr_tree::HostPath::kRing;
+    if (!R.ready) {
+        VR_CUDA(cudaStreamCreateWithFlags(&R.sr[0], cudaStreamNonBlocking));
+        VR_CUDA(cudaStreamCreateWithFlags(&R.sr[1], cudaStreamNonBlocking));
+        VR_CUDA(cudaStreamCreateWithFlags(&R.sc, cudaStreamNonBlocking));
+        for (int i = 0; i < kRing; ++i) {
+            VR_CUDA(cudaEventCreateWithFlags(&R.rendered[i], cudaEventDisableTiming));
+            VR_CUDA(cudaEventCreateWithFlags(&R.copied[i], cudaEventDisableTiming));
         }
-    } R;
-    VR_CUDA(cudaStreamCreateWithFlags(&R.sr[0], cudaStreamNonBlocking));
-    VR_CUDA(cudaStreamCreateWithFlags(&R.sr[1], cudaStreamNonBlocking));
-    VR_CUDA(cudaStreamCreateWithFlags(&R.sc, cudaStreamNonBlocking));
-    for (int i = 0; i < kRing; ++i) {
-        VR_CUDA(cudaMalloc(&R.buf[i], frame * chunk));
-        VR_CUDA(cudaEventCreateWithFlags(&R.rendered[i], cudaEventDisableTiming));
-        VR_CUDA(cudaEventCreateWithFlags(&R.copied[i], cudaEventDisableTiming));
+        R.ready = true;
+    }
+    if (R.buf_bytes < frame * chunk) {
+        for (int i = 0; i < kRing; ++i) { cudaFree(R.buf[i]); R.buf[i] = nullptr; }
+        R.buf_bytes = 0;
+        for (int i = 0; i < kRing; ++i) VR_CUDA(cudaMalloc(&R.buf[i], frame * chunk));
+        R.buf_bytes = frame * chunk;
     }
     int c = 0;
     for (int v0 = 0; v0 < n_views; v0 += chunk, ++c) {

@@ -16,6 +16,7 @@ struct LaunchCfg {
     unsigned int* queue;  // persistent kernels: {work head, done CTAs}
     const void* l2_window;   // optional persisting-L2 access window (the node table)
     size_t l2_window_bytes;  // 0 = none
+    bool pdl;                // allow overlap with the previous launch of the stream (see vr_march.cuh)
     cudaStream_t stream;
 };
 

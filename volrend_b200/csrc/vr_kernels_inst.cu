@@ -43,22 +43,26 @@ cudaError_t launch_persistent(LaunchDev& P, const LaunchCfg& cfg) {
     const int need = (P.n_tiles + (kBlock / 32) - 1) / (kBlock / 32);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    if (cfg.l2_window_bytes) {
-        // keep the node table resident in the persisting part of L2 across frames
-        cudaLaunchConfig_t lc{};
-        lc.gridDim = dim3(grid); lc.blockDim = dim3(kBlock); lc.dynamicSmemBytes = smem; lc.stream = cfg.stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(cfg.l2_window);
-        attr[0].val.accessPolicyWindow.num_bytes = cfg.l2_window_bytes;
-        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
-        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        lc.attrs = attr; lc.numAttrs = 1;
-        return cudaLaunchKernelEx(&lc, march_persistent_kernel<KBD, TOP, COUNT, OUT, TUNE>, P);
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(kBlock); lc.dynamicSmemBytes = smem; lc.stream = cfg.stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cfg.pdl) {  // programmatic dependent launch: see pdl_wait_predecessor() in vr_march.cuh
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
     }
-    march_persistent_kernel<KBD, TOP, COUNT, OUT, TUNE><<<grid, kBlock, smem, cfg.stream>>>(P);
-    return cudaGetLastError();
+    if (cfg.l2_window_bytes) {  // keep the node table resident in the persisting part of L2
+        attr[na].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[na].val.accessPolicyWindow.base_ptr = const_cast<void*>(cfg.l2_window);
+        attr[na].val.accessPolicyWindow.num_bytes = cfg.l2_window_bytes;
+        attr[na].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        ++na;
+    }
+    lc.attrs = attr; lc.numAttrs = na;
+    return cudaLaunchKernelEx(&lc, march_persistent_kernel<KBD, TOP, COUNT, OUT, TUNE>, P);
 }
 
 template <int KBD, bool TOP, bool COUNT, int OUT>
