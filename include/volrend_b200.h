@@ -126,6 +126,14 @@ int vr_render_composite(const vr_tree* tree, const vr_camera* cam, const vr_opti
 int vr_render_surface(const vr_tree* tree, const vr_camera* cam, const vr_options* opt,
                       unsigned long long rgba8_surf, unsigned long long depth_surf, void* stream);
 
+/* Ray-tile sharding of one frame across n_parts GPUs: this call renders every
+ * n_parts-th band of band_h rows (bands part, part+n_parts, ...) of the full frame and writes them
+ * compactly, band after band, into rgba8_dev / rgba32f_dev (vr_band_rows() rows of cam->width
+ * pixels).  One launch per GPU per frame; the caller gathers the compact buffers. */
+int vr_render_bands(const vr_tree* tree, const vr_camera* cam, const vr_options* opt, int band_h, int n_parts,
+                    int part, uint8_t* rgba8_dev, float* rgba32f_dev, void* stream);
+int vr_band_rows(int height, int band_h, int n_parts, int part);
+
 /* Host-buffer entry point: renders n_views full frames and copies each to
  * rgba8_host + i*4*w*h (pinned or pageable); returns after the last copy completed. */
 int vr_render_frames_host(const vr_tree* tree, const vr_camera* cams, int n_views,

@@ -51,15 +51,18 @@ def _worker(rank, world, port, W, H, n_views, q):
     def cam(i):
         return ob.make_camera(W, H, synth.focal_for(W), synth.focal_for(W), synth.c2w_to_colmajor12(poses[i]))
 
-    def render_rect(rect):
-        _, u, _ = ob.render(ot, cam(1), opt, tile=rect, want_float=False, nthreads=1)
-        return torch.from_numpy(u)
+    def render_part(band_h, n_parts, part):
+        # stand-in for vr_render_bands: this part's bands, compactly, band after band
+        rows = [ob.render(ot, cam(1), opt, tile=r, want_float=False, nthreads=1)[1]
+                for r in vd.shard_bands(W, H, part, n_parts, band_h)]
+        return torch.from_numpy(np.concatenate(rows, 0) if rows else np.zeros((0, W, 4), np.uint8))
 
     def render_views(idx):
         return torch.from_numpy(np.stack([ob.render(ot, cam(i), opt, want_float=False, nthreads=1)[1] for i in idx])
                                 if idx else np.zeros((0, H, W, 4), np.uint8))
 
-    frame = vd.render_tile_sharded(render_rect, W, H, rank, world, band_h=8)
+    frame = vd.render_tile_sharded(render_part, W, H, rank, world, band_h=8)
+    assert vd.band_rows(H, 8, world, rank) == sum(r[3] for r in vd.shard_bands(W, H, rank, world, 8))
     views = vd.render_view_sharded(render_views, n_views, rank, world)
     if rank == 0:
         full = ob.render(ot, cam(1), opt, want_float=False, nthreads=1)[1]
@@ -76,7 +79,8 @@ def test_tile_and_view_sharding_reassemble_bit_exact(built, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 40, 36, 5, q)) for r in range(world)]
+    H = 36 if world == 3 else 48      # 36 rows: ragged bands; 48 rows / world 2: the regular strided path
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 40, H, 5, q)) for r in range(world)]
     for p in procs:
         p.start()
     ok_tiles, ok_views = q.get(timeout=120)

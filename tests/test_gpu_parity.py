@@ -373,3 +373,29 @@ def test_back_to_back_launches_keep_stream_order(built, dev_trees):
     torch.cuda.synchronize()
     _, want, _ = oracle_render(st, cams[1], {}, rgba_in=solo[0], depth_in=np.full((160, 200), 1e9, np.float32))
     assert (img.cpu().numpy() != want).any(-1).sum() <= 2
+
+
+def test_render_bands_matches_full_frame(built, dev_trees):
+    """vr_render_bands: every part's compact buffer holds exactly its interleaved bands."""
+    torch = _torch()
+    from volrend_b200 import RenderOptions, render_bands, synth
+    from volrend_b200 import dist as vd
+    st, tree = dev_trees["sh9_d6"]
+    cam = make_cam(120, 92, synth.nerf_synthetic_test_poses(8)[4])       # 92 rows: ragged last band
+    f_full, u_full, _ = gpu_render(tree, cam, RenderOptions())
+    for world, band_h in ((1, 8), (2, 8), (3, 4), (4, 16)):
+        seen = np.zeros(92, int)
+        for part in range(world):
+            rows = vd.band_rows(92, band_h, world, part)
+            img = torch.zeros((max(rows, 1), 120, 4), dtype=torch.uint8, device="cuda")
+            fo = torch.zeros((max(rows, 1), 120, 4), dtype=torch.float32, device="cuda")
+            got = render_bands(tree, cam, RenderOptions(), band_h, world, part, img, float_out=fo)
+            torch.cuda.synchronize()
+            assert got == rows
+            r0 = 0
+            for (x0, y0, w, h) in vd.shard_bands(120, 92, part, world, band_h):
+                assert np.array_equal(img[r0:r0 + h].cpu().numpy(), u_full[y0:y0 + h])
+                assert np.array_equal(fo[r0:r0 + h].cpu().numpy(), f_full[y0:y0 + h])
+                seen[y0:y0 + h] += 1
+                r0 += h
+        assert np.all(seen == 1)

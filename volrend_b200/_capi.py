@@ -68,6 +68,9 @@ SYMBOLS = {
     "vr_render_frames_host": (C.c_int, [C.c_void_p, C.POINTER(vr_camera), C.c_int, C.POINTER(vr_options),
                                         C.c_void_p]),
     "vr_probe_lumisphere": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
+    "vr_render_bands": (C.c_int, [C.c_void_p, C.POINTER(vr_camera), C.POINTER(vr_options), C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vr_band_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "vr_debug_trace": (C.c_int, [C.c_void_p, C.POINTER(vr_camera), C.POINTER(vr_options), C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
     "vr_set_variant": (C.c_int, [C.c_int]),

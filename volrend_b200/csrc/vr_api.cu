@@ -471,6 +471,37 @@ int vr_render_batch(const vr_tree* t, const vr_camera* cams, int n_views, const 
     return dispatch(t, P, counters_dev != nullptr, false, stream);
 }
 
+int vr_render_bands(const vr_tree* t, const vr_camera* cam, const vr_options* opt, int band_h, int n_parts,
+                    int part, uint8_t* rgba8_dev, float* rgba32f_dev, void* stream_) {
+    vr_rect r;
+    int rc = check_common(t, cam, opt, nullptr, r);
+    if (rc) return rc;
+    if (band_h < 4 || band_h % 4 || n_parts < 1 || part < 0 || part >= n_parts)
+        return fail(VR_EINVAL, "bands: band_h must be a positive multiple of 4 and 0 <= part < n_parts");
+    const int rows = vr_band_rows(cam->height, band_h, n_parts, part);
+    if (rows == 0) return VR_OK;
+    LaunchDev P{};
+    P.tree = t->dev;
+    fill_opt(P.opt, opt);
+    fill_cam(P.cam, cam);
+    P.n_views = 1;
+    P.x0 = 0; P.y0 = 0; P.w = r.w; P.h = rows;
+    P.band_h = band_h; P.band_parts = n_parts; P.band_part = part;
+    P.rgba8 = rgba8_dev; P.rgbaf = reinterpret_cast<float4*>(rgba32f_dev);
+    return dispatch(t, P, false, false, (cudaStream_t)stream_);
+}
+
+int vr_band_rows(int height, int band_h, int n_parts, int part) {
+    if (height <= 0 || band_h <= 0 || n_parts <= 0 || part < 0 || part >= n_parts) return 0;
+    const int n_bands = (height + band_h - 1) / band_h;
+    int rows = 0;
+    for (int b = part; b < n_bands; b += n_parts) {
+        const int y = b * band_h;
+        rows += (height - y < band_h) ? height - y : band_h;
+    }
+    return rows;
+}
+
 int vr_debug_trace(const vr_tree* t, const vr_camera* cam, const vr_options* opt, uint8_t* rgba8_dev,
                    vr_counters* counters_dev, unsigned long long* trace_dev, void* stream_) {
     vr_rect r;

@@ -59,7 +59,9 @@ struct LaunchDev {
     CamDev cam;            // used when cams == nullptr
     const CamDev* cams;    // device array for batches
     int32_t n_views;
-    int32_t x0, y0, w, h;  // tile inside the cam.width x cam.height frame
+    int32_t x0, y0, w, h;  // tile inside the cam.width x cam.height frame (h = rows of the output buffer)
+    int32_t band_h, band_parts, band_part;  // ray-tile sharding: output row r is frame row
+                                            // y0 + ((r/band_h)*band_parts + band_part)*band_h + r%band_h
     uint8_t* rgba8;        // linear tile-sized RGBA8 per view (or nullptr)
     float4* rgbaf;         // linear tile-sized float4 per view (or nullptr)
     const float* depth_in; // composite mode: per-pixel t limit (world units)

@@ -46,33 +46,55 @@ def merge_adjacent(rects: Sequence[Rect]) -> List[Rect]:
     return out
 
 
-def render_tile_sharded(render_rect: Callable[[Rect], "torch.Tensor"], width: int, height: int, rank: int,
+def band_rows(height: int, band_h: int, world: int, rank: int) -> int:
+    """Rows owned by ``rank`` (== vr_band_rows in the C-ABI)."""
+    return sum(r[3] for r in shard_bands(1, height, rank, world, band_h))
+
+
+def render_tile_sharded(render_part: Callable[[int, int, int], "torch.Tensor"], width: int, height: int, rank: int,
                         world: int, band_h: int = 8, dst: int = 0, group=None):
-    """Render this rank's bands with ``render_rect(rect) -> uint8 [h,w,4]`` and gather the whole
-    frame on ``dst``.  Returns the [H,W,4] frame on dst, None elsewhere."""
+    """``render_part(band_h, world, rank) -> uint8 [rows, W, 4]``: this rank's bands rendered
+    compactly by ONE launch (``volrend_b200.render_bands`` / ``vr_render_bands``).  Gathers the
+    compact buffers on ``dst`` and interleaves them into the [H,W,4] frame (None elsewhere)."""
     import torch
     import torch.distributed as dist
-    mine = shard_bands(width, height, rank, world, band_h)
-    parts = [render_rect(r) for r in mine]
-    n_bands = len(band_rects(width, height, band_h))
-    per_rank = (n_bands + world - 1) // world
-    # equal-sized messages: pad the band list of the ranks that own one band fewer
-    dev = parts[0].device if parts else torch.device("cpu")
-    local = torch.zeros((per_rank, band_h, width, 4), dtype=torch.uint8, device=dev)
-    for i, (r, p) in enumerate(zip(mine, parts)):
-        local[i, : r[3]] = p
+    part = render_part(band_h, world, rank)
+    rows_max = band_rows(height, band_h, world, 0)          # rank 0 owns the most bands
+    local = part
+    if part.shape[0] < rows_max:                             # equal-sized messages
+        local = torch.zeros((rows_max, width, 4), dtype=torch.uint8, device=part.device)
+        local[: part.shape[0]] = part
     if world == 1:
         gathered = [local]
     else:
         gathered = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
-        dist.gather(local, gathered, dst=dst, group=group)
+        dist.gather(local.contiguous(), gathered, dst=dst, group=group)
         if rank != dst:
             return None
-    frame = torch.empty((height, width, 4), dtype=torch.uint8, device=dev)
-    for rk in range(world):
-        for i, r in enumerate(shard_bands(width, height, rk, world, band_h)):
-            frame[r[1]: r[1] + r[3]] = gathered[rk][i, : r[3]]
+    frame = torch.empty((height, width, 4), dtype=torch.uint8, device=part.device)
+    full_bands = height // band_h
+    if full_bands % world == 0 and height % band_h == 0:
+        # regular case: one strided copy per rank
+        fv = frame.view(full_bands // world, world, band_h, width, 4)
+        for rk in range(world):
+            fv[:, rk] = gathered[rk][: (full_bands // world) * band_h].view(full_bands // world, band_h, width, 4)
+        return frame
+    for rk in range(world):   # ragged case: one index_copy per rank (row indices cached)
+        idx = _band_row_index(height, band_h, world, rk, part.device)
+        frame.index_copy_(0, idx, gathered[rk][: idx.numel()])
     return frame
+
+
+_ROW_INDEX_CACHE: dict = {}
+
+
+def _band_row_index(height: int, band_h: int, world: int, rank: int, device):
+    import torch
+    key = (height, band_h, world, rank, str(device))
+    if key not in _ROW_INDEX_CACHE:
+        rows = [y for r in shard_bands(1, height, rank, world, band_h) for y in range(r[1], r[1] + r[3])]
+        _ROW_INDEX_CACHE[key] = torch.tensor(rows, dtype=torch.long, device=device)
+    return _ROW_INDEX_CACHE[key]
 
 
 def render_view_sharded(render_views: Callable[[List[int]], "torch.Tensor"], n_views: int, rank: int, world: int,

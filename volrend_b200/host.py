@@ -346,6 +346,17 @@ def launch_renderer(tree: N3Tree, cam: Camera, options: RenderOptions, image_arr
                                         depth_arr.data_ptr(), fo, s))
 
 
+def render_bands(tree: N3Tree, cam: Camera, options: RenderOptions, band_h: int, n_parts: int, part: int,
+                 image, *, float_out=None, stream=None) -> int:
+    """Ray-tile sharding: render bands part, part+n_parts, ... (band_h rows each) of the frame into the
+    compact ``image`` (uint8 [rows, W, 4]); returns the number of rows this part owns."""
+    c, o = cam._as_c(), options._as_c()
+    check(lib().vr_render_bands(tree._handle, C.byref(c), C.byref(o), int(band_h), int(n_parts), int(part),
+                                image.data_ptr() if image is not None else None,
+                                float_out.data_ptr() if float_out is not None else None, _stream_ptr(stream)))
+    return lib().vr_band_rows(cam.height, int(band_h), int(n_parts), int(part))
+
+
 def render_batch(tree: N3Tree, cams, options: RenderOptions, images, *, float_out=None, counters=None,
                  tile=None, stream=None) -> None:
     """The pose loop of main_headless.cpp:208-223 as one call; ``images``: uint8 [V,H,W,4]."""
