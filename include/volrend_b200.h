@@ -98,9 +98,24 @@ typedef struct {
     int64_t node_bytes, rec_total_bytes, top_bytes;
 } vr_tree_info;
 
+/* Compressed N3Tree as written by scripts/compress_octree.py:93-118 (keys quant_colors, quant_map,
+ * sigma, data_retained).  The reference decodes it on the CPU with a scalar loop at load time
+ * (src/n3tree.cpp:279-340); vr_tree_create_quantized uploads the compressed arrays and decodes on
+ * the GPU straight into the device layout (same resulting tree, bit for bit). */
+typedef struct {
+    vr_tree_desc base;             /* child + header fields; base.data must be NULL */
+    const uint16_t* quant_colors;  /* fp16 [n_quant][65536][3] codebooks */
+    const uint16_t* quant_map;     /* u16  [n_quant][capacity*N^3] codebook indices */
+    const uint16_t* sigma;         /* fp16 [capacity*N^3] */
+    const uint16_t* data_retained; /* fp16 [n_retain][capacity*N^3][3] or NULL */
+    int32_t n_quant;               /* quantised basis functions */
+    int32_t n_retain;              /* un-quantised leading basis functions (n_quant+n_retain == basis_dim) */
+} vr_tree_quant_desc;
+
 void vr_default_options(vr_options* o);
 
 int vr_tree_create(const vr_tree_desc* desc, vr_tree** out);
+int vr_tree_create_quantized(const vr_tree_quant_desc* desc, vr_tree** out);
 void vr_tree_destroy(vr_tree* tree);
 int vr_tree_get_info(const vr_tree* tree, vr_tree_info* info);
 

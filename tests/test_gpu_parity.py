@@ -399,3 +399,38 @@ def test_render_bands_matches_full_frame(built, dev_trees):
                 seen[y0:y0 + h] += 1
                 r0 += h
         assert np.all(seen == 1)
+
+
+def test_gpu_decode_of_quantised_tree(built, tmp_path):
+    """vr_tree_create_quantized (GPU decode of quant_colors/quant_map/sigma/data_retained) gives the
+    same device tree as the reference's CPU decode (src/n3tree.cpp:279-340): identical renders,
+    identical probed coefficients, also against the reference loader + kernel when present."""
+    torch = _torch()
+    from volrend_b200 import N3Tree, RenderOptions, lib, synth
+    from volrend_b200._capi import check
+    for basis, n_retain, fmt in ((16, 1, "SH"), (9, 0, "SH"), (7, 2, "SG")):
+        st = synth.make_tree("lego", depth=6, basis_dim=basis, seed=basis, fmt=fmt)
+        npz = synth.quantise_tree(st, n_retain=n_retain, seed=3)
+        path = str(tmp_path / f"q{basis}.npz")
+        np.savez(path, **npz)
+        t_gpu, t_cpu = N3Tree(path, gpu_decode=True), N3Tree(path, gpu_decode=False)
+        assert t_gpu._data is None                      # nothing was decoded on the host
+        cam = make_cam(96, 80, synth.nerf_synthetic_test_poses(8)[3])
+        fg, ug, _ = gpu_render(t_gpu, cam, RenderOptions())
+        fc, uc, _ = gpu_render(t_cpu, cam, RenderOptions())
+        assert np.array_equal(fg, fc) and np.array_equal(ug, uc)
+        if basis in (1, 4, 9, 16, 25):
+            out_g = torch.zeros(3 * basis, dtype=torch.float32, device="cuda")
+            out_c = torch.zeros(3 * basis, dtype=torch.float32, device="cuda")
+            arr = (C.c_float * 3)(0.05, -0.1, 0.02)
+            check(lib().vr_probe_lumisphere(t_gpu._handle, arr, out_g.data_ptr(), None))
+            check(lib().vr_probe_lumisphere(t_cpu._handle, arr, out_c.data_ptr(), None))
+            torch.cuda.synchronize()
+            assert torch.equal(out_g, out_c)
+        from oracle import ref_binding as rb
+        if rb.available() and fmt == "SH":
+            rt = rb.RefTree(path)                       # reference loader decodes on the CPU
+            c12 = np.ascontiguousarray(cam.transform, np.float32).reshape(12)
+            fr = rt.render_f32(96, 80, cam.fx, cam.fy, c12, rb.make_options())
+            rt.close()
+            assert np.array_equal(fg, fr)

@@ -128,3 +128,17 @@ def test_pose_files_roundtrip(synth_mod, tmp_path):
     K = np.loadtxt(os.path.join(str(tmp_path), "intrinsics.txt"))
     assert abs(K[0, 0] - 1111.11) < 1e-3 and abs(K[1, 1] - 1111.11) < 1e-3
     np.testing.assert_allclose(np.linalg.norm(poses[:, :3, 3], axis=1), 4.031128874, rtol=1e-5)
+
+
+def test_quantised_file_lazy_decode_equals_eager(synth_mod):
+    st = synth_mod.make_tree("lego", depth=4, basis_dim=9, seed=5)
+    npz = synth_mod.quantise_tree(st, n_retain=2, seed=1)
+    lazy, eager = N3Tree(gpu_decode=True), N3Tree(gpu_decode=False)
+    lazy.load_npz(dict(npz))
+    eager.load_npz(dict(npz))
+    assert lazy._data is None and lazy.quant_ is not None and eager._data is not None
+    np.testing.assert_array_equal(lazy.data_.view(np.uint16), eager.data_.view(np.uint16))
+    # sigma survives, and the retained functions land in the leading slots of each channel
+    np.testing.assert_array_equal(eager.data_[..., -1].view(np.uint16), st.data[..., -1].view(np.uint16))
+    np.testing.assert_array_equal(eager.data_[..., 9 + 1].view(np.uint16),
+                                  npz["data_retained"][1][..., 1].view(np.uint16))

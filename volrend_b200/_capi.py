@@ -26,6 +26,11 @@ class vr_tree_desc(C.Structure):
                 ("ndc_width", C.c_float), ("ndc_height", C.c_float), ("ndc_focal", C.c_float)]
 
 
+class vr_tree_quant_desc(C.Structure):
+    _fields_ = [("base", vr_tree_desc), ("quant_colors", C.c_void_p), ("quant_map", C.c_void_p),
+                ("sigma", C.c_void_p), ("data_retained", C.c_void_p), ("n_quant", C.c_int32), ("n_retain", C.c_int32)]
+
+
 class vr_camera(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
                 ("c2w", C.c_float * 12)]
@@ -55,6 +60,7 @@ class vr_tree_info(C.Structure):
 SYMBOLS = {
     "vr_default_options": (None, [C.POINTER(vr_options)]),
     "vr_tree_create": (C.c_int, [C.POINTER(vr_tree_desc), C.POINTER(C.c_void_p)]),
+    "vr_tree_create_quantized": (C.c_int, [C.POINTER(vr_tree_quant_desc), C.POINTER(C.c_void_p)]),
     "vr_tree_destroy": (None, [C.c_void_p]),
     "vr_tree_get_info": (C.c_int, [C.c_void_p, C.POINTER(vr_tree_info)]),
     "vr_render": (C.c_int, [C.c_void_p, C.POINTER(vr_camera), C.POINTER(vr_options), C.POINTER(vr_rect),

@@ -138,6 +138,70 @@ __global__ void relayout_recs_kernel(const unsigned short* __restrict__ data, un
     reinterpret_cast<uint4*>(recs + (size_t)slot * rec_bytes)[chunk] = v;
 }
 
+// Quantised trees (scripts/compress_octree.py; CPU decode in src/n3tree.cpp:309-340):
+//   data[slot][j + n_retain + k*n_total] = quant_colors[j][quant_map[j][slot]][k]   j < n_quant
+//   data[slot][j + k*n_total]            = data_retained[j][slot][k]                j < n_retain
+//   data[slot][data_dim-1]               = sigma[slot]
+// decoded here straight into the padded records / node words.
+__global__ void quant_nodes_kernel(const int32_t* __restrict__ child, const unsigned short* __restrict__ sigma,
+                                   uint32_t* __restrict__ nodes, long long n_slots, long long capacity,
+                                   int* __restrict__ bad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    const int32_t rel = child[i];
+    if (rel != 0) {
+        const long long tgt = (i >> 3) + rel;
+        if (tgt <= 0 || tgt >= capacity) {
+            atomicExch(bad, 1);
+            nodes[i] = kLeafBit;
+        } else {
+            nodes[i] = (uint32_t)tgt;
+        }
+    } else {
+        nodes[i] = kLeafBit | (uint32_t)sigma[i];
+    }
+}
+
+__device__ __forceinline__ unsigned short quant_coeff(const unsigned short* __restrict__ colors,
+                                                      const unsigned short* __restrict__ qmap,
+                                                      const unsigned short* __restrict__ retained, long long n_slots,
+                                                      long long slot, int n_retain, int j, int k) {
+    if (j < n_retain) return retained[((size_t)j * n_slots + slot) * 3 + k];
+    const int q = j - n_retain;
+    const unsigned int id = qmap[(size_t)q * n_slots + slot];
+    return colors[((size_t)q * 65536 + id) * 3 + k];
+}
+
+__global__ void quant_recs_kernel(const unsigned short* __restrict__ colors, const unsigned short* __restrict__ qmap,
+                                  const unsigned short* __restrict__ retained, unsigned char* __restrict__ recs,
+                                  long long n_slots, int n_total, int n_retain, int kbd, int rec_bytes) {
+    const int chunks = rec_bytes >= 16 ? rec_bytes / 16 : 1;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long slot = gid / chunks;
+    const int chunk = (int)(gid % chunks);
+    if (slot >= n_slots) return;
+    if (rec_bytes == 8) {  // one coefficient per channel (basis sizes the reference's switch ignores)
+        ushort4 v;
+        v.x = quant_coeff(colors, qmap, retained, n_slots, slot, n_retain, 0, 0);
+        v.y = quant_coeff(colors, qmap, retained, n_slots, slot, n_retain, 0, 1);
+        v.z = quant_coeff(colors, qmap, retained, n_slots, slot, n_retain, 0, 2);
+        v.w = 0;
+        reinterpret_cast<ushort4*>(recs)[slot] = v;
+        return;
+    }
+    unsigned short h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = chunk * 8 + i;                 // record half index = k*kbd + j (kbd == n_total here)
+        h[i] = c < 3 * kbd ? quant_coeff(colors, qmap, retained, n_slots, slot, n_retain, c % n_total, c / n_total)
+                           : (unsigned short)0;
+    }
+    uint4 v;
+    v.x = h[0] | ((uint32_t)h[1] << 16); v.y = h[2] | ((uint32_t)h[3] << 16);
+    v.z = h[4] | ((uint32_t)h[5] << 16); v.w = h[6] | ((uint32_t)h[7] << 16);
+    reinterpret_cast<uint4*>(recs + (size_t)slot * rec_bytes)[chunk] = v;
+}
+
 // depth[n] of every node by level-synchronous relaxation from the root.
 __global__ void node_depth_kernel(const uint32_t* __restrict__ nodes, int* __restrict__ depth, long long capacity,
                                   int level, int* __restrict__ changed) {
@@ -239,7 +303,7 @@ void vr_tree_destroy(vr_tree* t) {
     delete t;
 }
 
-int vr_tree_create(const vr_tree_desc* d, vr_tree** out) {
+static int tree_create_impl(const vr_tree_desc* d, const vr_tree_quant_desc* q, vr_tree** out) {
     if (!d || !out) return fail(VR_EINVAL, "null argument");
     *out = nullptr;
     int ndev = 0;
@@ -249,7 +313,14 @@ int vr_tree_create(const vr_tree_desc* d, vr_tree** out) {
     }
     if (d->N != 2) return fail(VR_EUNSUPPORTED, "N=%d: only N=2 octrees are supported (as in the reference)", d->N);
     if (d->capacity < 1 || d->capacity >= (1ll << 28)) return fail(VR_EINVAL, "capacity %lld out of range", (long long)d->capacity);
-    if (!d->child || !d->data) return fail(VR_EINVAL, "child/data arrays missing");
+    if (!d->child || (!q && !d->data)) return fail(VR_EINVAL, "child/data arrays missing");
+    if (q) {
+        if (!q->quant_colors || !q->quant_map || !q->sigma) return fail(VR_EINVAL, "quantised arrays missing");
+        if (q->n_quant < 1 || q->n_retain < 0 || (q->n_retain > 0 && !q->data_retained))
+            return fail(VR_EINVAL, "bad quantised basis counts");
+        if (d->format == VR_FMT_RGBA || q->n_quant + q->n_retain != d->basis_dim)
+            return fail(VR_EINVAL, "codebook and map basis numbers does not match");   // n3tree.cpp:296-299
+    }
     if (d->format < VR_FMT_RGBA || d->format > VR_FMT_ASG) return fail(VR_EINVAL, "bad data format %d", d->format);
     const int kbd = kernel_basis(d->format, d->basis_dim);
     if (kbd < 0 ? d->data_dim < 4 : d->data_dim < 3 * d->basis_dim + 1)
@@ -274,9 +345,9 @@ int vr_tree_create(const vr_tree_desc* d, vr_tree** out) {
     int* flags = nullptr;
     int* depth = nullptr;
     struct Tmp { int32_t*& a; unsigned short*& b; int*& c; int*& d; ~Tmp() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); } } tmp{raw_child, raw_data, flags, depth};
-    const size_t child_bytes = (size_t)n_slots * 4, data_bytes = (size_t)n_slots * d->data_dim * 2;
+    const size_t child_bytes = (size_t)n_slots * 4, data_bytes = q ? 0 : (size_t)n_slots * d->data_dim * 2;
     VR_CUDA(cudaMalloc(&raw_child, child_bytes));
-    VR_CUDA(cudaMalloc(&raw_data, data_bytes));
+    if (!q) VR_CUDA(cudaMalloc(&raw_data, data_bytes));
     VR_CUDA(cudaMalloc(&flags, 2 * sizeof(int)));
     VR_CUDA(cudaMalloc(&depth, (size_t)d->capacity * sizeof(int)));
     VR_CUDA(cudaMalloc(&t->nodes, (size_t)n_slots * 4));
@@ -286,7 +357,7 @@ int vr_tree_create(const vr_tree_desc* d, vr_tree** out) {
     VR_CUDA(cudaMemset(t->queues, 0, kQueueSlots * 2 * sizeof(unsigned int)));
     VR_CUDA(cudaMalloc(&t->cam_ring, kCamRing * sizeof(CamDev)));
     VR_CUDA(cudaMemcpy(raw_child, d->child, child_bytes, cudaMemcpyHostToDevice));
-    VR_CUDA(cudaMemcpy(raw_data, d->data, data_bytes, cudaMemcpyHostToDevice));
+    if (!q) VR_CUDA(cudaMemcpy(raw_data, d->data, data_bytes, cudaMemcpyHostToDevice));
     VR_CUDA(cudaMemset(flags, 0, 2 * sizeof(int)));
     if (d->extra && (d->format == VR_FMT_SG || d->format == VR_FMT_ASG)) {
         const size_t nf = (size_t)d->basis_dim * (d->format == VR_FMT_SG ? 4 : 11);
@@ -294,12 +365,31 @@ int vr_tree_create(const vr_tree_desc* d, vr_tree** out) {
         VR_CUDA(cudaMemcpy(t->extra, d->extra, nf * sizeof(float), cudaMemcpyHostToDevice));
     }
     const int TB = 256;
-    relayout_nodes_kernel<<<(unsigned)((n_slots + TB - 1) / TB), TB>>>(raw_child, raw_data, t->nodes, n_slots,
-                                                                       d->capacity, d->data_dim, flags);
-    {
-        const long long work = n_slots * (rec_bytes >= 16 ? rec_bytes / 16 : 1);
-        relayout_recs_kernel<<<(unsigned)((work + TB - 1) / TB), TB>>>(raw_data, t->recs, n_slots, d->data_dim,
-                                                                       d->basis_dim, kbd, rec_bytes);
+    const long long rec_work = n_slots * (rec_bytes >= 16 ? rec_bytes / 16 : 1);
+    unsigned short *q_colors = nullptr, *q_map = nullptr, *q_sigma = nullptr, *q_ret = nullptr;
+    struct QTmp { unsigned short *&a, *&b, *&c, *&d; ~QTmp() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); } } qtmp{q_colors, q_map, q_sigma, q_ret};
+    if (!q) {
+        relayout_nodes_kernel<<<(unsigned)((n_slots + TB - 1) / TB), TB>>>(raw_child, raw_data, t->nodes, n_slots,
+                                                                           d->capacity, d->data_dim, flags);
+        relayout_recs_kernel<<<(unsigned)((rec_work + TB - 1) / TB), TB>>>(raw_data, t->recs, n_slots, d->data_dim,
+                                                                           d->basis_dim, kbd, rec_bytes);
+    } else {
+        const size_t cb = (size_t)q->n_quant * 65536 * 3 * 2, mb = (size_t)q->n_quant * n_slots * 2,
+                     sb = (size_t)n_slots * 2, rb = (size_t)q->n_retain * n_slots * 3 * 2;
+        VR_CUDA(cudaMalloc(&q_colors, cb));
+        VR_CUDA(cudaMalloc(&q_map, mb));
+        VR_CUDA(cudaMalloc(&q_sigma, sb));
+        VR_CUDA(cudaMemcpy(q_colors, q->quant_colors, cb, cudaMemcpyHostToDevice));
+        VR_CUDA(cudaMemcpy(q_map, q->quant_map, mb, cudaMemcpyHostToDevice));
+        VR_CUDA(cudaMemcpy(q_sigma, q->sigma, sb, cudaMemcpyHostToDevice));
+        if (q->n_retain > 0) {
+            VR_CUDA(cudaMalloc(&q_ret, rb));
+            VR_CUDA(cudaMemcpy(q_ret, q->data_retained, rb, cudaMemcpyHostToDevice));
+        }
+        quant_nodes_kernel<<<(unsigned)((n_slots + TB - 1) / TB), TB>>>(raw_child, q_sigma, t->nodes, n_slots,
+                                                                        d->capacity, flags);
+        quant_recs_kernel<<<(unsigned)((rec_work + TB - 1) / TB), TB>>>(q_colors, q_map, q_ret, t->recs, n_slots,
+                                                                        d->basis_dim, q->n_retain, kbd, rec_bytes);
     }
     VR_CUDA(cudaGetLastError());
     int h_flags[2] = {0, 0};
@@ -349,6 +439,14 @@ int vr_tree_create(const vr_tree_desc* d, vr_tree** out) {
     guard.ok = true;
     *out = t;
     return VR_OK;
+}
+
+int vr_tree_create(const vr_tree_desc* d, vr_tree** out) { return tree_create_impl(d, nullptr, out); }
+
+int vr_tree_create_quantized(const vr_tree_quant_desc* q, vr_tree** out) {
+    if (!q) return fail(VR_EINVAL, "null argument");
+    if (q->base.data) return fail(VR_EINVAL, "quantised descriptor must not carry decoded data");
+    return tree_create_impl(&q->base, q, out);
 }
 
 int vr_tree_get_info(const vr_tree* t, vr_tree_info* info) {

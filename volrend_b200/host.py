@@ -69,7 +69,12 @@ class DataFormat:
 class N3Tree:
     """Read-only N3Tree: npz loader + device upload (re-layout happens in ``load_cuda``)."""
 
-    def __init__(self, path: str | None = None):
+    def __init__(self, path: str | None = None, gpu_decode: bool = True):
+        # gpu_decode: quantised files (quant_colors/quant_map/...) are decoded by the GPU at upload
+        # (vr_tree_create_quantized) instead of the reference's CPU loop; ``data_`` then decodes
+        # lazily on first access.
+        self.gpu_decode = gpu_decode
+        self.quant_ = None      # compressed arrays of a quantised file
         self.N = 0
         self.data_dim = 0
         self.data_format = DataFormat()
@@ -78,7 +83,7 @@ class N3Tree:
         self.offset = np.zeros(3, np.float32)
         self.use_ndc = False
         self.ndc_width = self.ndc_height = self.ndc_focal = 0.0
-        self.data_ = None       # fp16 [cap,N,N,N,data_dim]
+        self._data = None       # fp16 [cap,N,N,N,data_dim]  (see the data_ property)
         self.child_ = None      # int32 [cap,N,N,N]
         self.extra_ = None      # f32
         self._handle = None     # vr_tree*
@@ -86,6 +91,17 @@ class N3Tree:
         self._cuda_loaded = False
         if path is not None:
             self.open(path)
+
+    @property
+    def data_(self):
+        """N3Tree::data_ (fp16 [capacity,N,N,N,data_dim]); decoded on demand for quantised files."""
+        if self._data is None and self.quant_ is not None:
+            self._data = self._decode_quantised()
+        return self._data
+
+    @data_.setter
+    def data_(self, v):
+        self._data = v
 
     # -- reference surface
     def is_data_loaded(self) -> bool:
@@ -95,7 +111,7 @@ class N3Tree:
         return self._cuda_loaded
 
     def clear_cpu_memory(self) -> None:
-        self.data_ = None       # n3tree.cpp:441-447 keeps child_
+        self._data = None       # n3tree.cpp:441-447 keeps child_
 
     def open(self, path: str) -> None:
         """src/n3tree.cpp:111-154.  A missing file leaves the tree unloaded, like the reference."""
@@ -156,6 +172,8 @@ class N3Tree:
         self.N = int(self.child_.shape[1])
         if self.N != 2:
             print("WARNING: N != 2 probably doesn't work.")
+        self.quant_ = None
+        self._data = None
         if "quant_colors" in npz:
             qc = np.asarray(npz["quant_colors"])
             if qc.dtype.itemsize != 2:
@@ -167,29 +185,39 @@ class N3Tree:
                 raise RuntimeError("codebook and map basis numbers does not match")
             retained = np.asarray(npz["data_retained"]) if "data_retained" in npz else None
             n_retain = 0 if retained is None else int(retained.shape[0])
-            n_total = n_basis + n_retain
             n_child = self.capacity * self.N ** 3
-            data = np.zeros((n_child, self.data_dim), np.float16)
-            qc = qc.view(np.float16).reshape(n_basis, 65536, 3)
-            qm = qmap.reshape(n_basis, n_child)
-            for j in range(n_basis):
-                cols = qc[j][qm[j].astype(np.int64)]              # [n_child,3]
-                for k in range(3):
-                    data[:, j + n_retain + k * n_total] = cols[:, k]
-            data[:, self.data_dim - 1] = np.asarray(npz["sigma"]).view(np.float16).reshape(n_child)
-            if retained is not None:
-                rt = retained.view(np.float16).reshape(n_retain, n_child, 3)
-                for j in range(n_retain):
-                    for k in range(3):
-                        data[:, j + k * n_total] = rt[j, :, k]
-            self.data_ = data.reshape(self.capacity, self.N, self.N, self.N, self.data_dim)
+            self.quant_ = dict(
+                colors=np.ascontiguousarray(qc.view(np.uint16).reshape(n_basis, 65536, 3)),
+                map=np.ascontiguousarray(qmap.astype(np.uint16, copy=False).reshape(n_basis, n_child)),
+                sigma=np.ascontiguousarray(np.asarray(npz["sigma"]).view(np.uint16).reshape(n_child)),
+                retained=None if retained is None else np.ascontiguousarray(retained.view(np.uint16).reshape(n_retain, n_child, 3)),
+                n_quant=n_basis, n_retain=n_retain)
+            if not self.gpu_decode:
+                self._data = self._decode_quantised()
         else:
             data = np.asarray(npz["data"])
             self.capacity = int(data.shape[0])
             if data.dtype.itemsize != 2:
                 raise RuntimeError("data must be stored in half precision")
-            self.data_ = np.ascontiguousarray(data.view(np.float16))
+            self._data = np.ascontiguousarray(data.view(np.float16))
         self.extra_ = np.ascontiguousarray(np.asarray(npz["extra_data"], np.float32)) if "extra_data" in npz else None
+
+    def _decode_quantised(self) -> np.ndarray:
+        """Vectorised form of the scalar decode loops of src/n3tree.cpp:309-340."""
+        q = self.quant_
+        n_basis, n_retain = q["n_quant"], q["n_retain"]
+        n_total = n_basis + n_retain
+        n_child = self.capacity * self.N ** 3
+        data = np.zeros((n_child, self.data_dim), np.uint16)
+        for j in range(n_basis):
+            cols = q["colors"][j][q["map"][j].astype(np.int64)]      # [n_child,3]
+            for k in range(3):
+                data[:, j + n_retain + k * n_total] = cols[:, k]
+        data[:, self.data_dim - 1] = q["sigma"]
+        for j in range(n_retain):
+            for k in range(3):
+                data[:, j + k * n_total] = q["retained"][j, :, k]
+        return data.view(np.float16).reshape(self.capacity, self.N, self.N, self.N, self.data_dim)
 
     def _unpack_llff_poses_bounds(self, pb: np.ndarray) -> None:
         """src/n3tree.cpp:22-52 (only the fields the ray path uses)."""
@@ -199,10 +227,13 @@ class N3Tree:
     # -- device side (replaces src/cuda/n3tree.cu)
     def load_cuda(self) -> None:
         self.free_cuda()
-        d = _capi.vr_tree_desc()
+        use_quant = self.quant_ is not None and self.gpu_decode
+        qd = _capi.vr_tree_quant_desc() if use_quant else None
+        d = qd.base if use_quant else _capi.vr_tree_desc()
         d.child = self.child_.ctypes.data
-        data = np.ascontiguousarray(self.data_)
-        d.data = data.ctypes.data
+        if not use_quant:
+            data = np.ascontiguousarray(self.data_)
+            d.data = data.ctypes.data
         d.extra = self.extra_.ctypes.data if self.extra_ is not None else None
         d.capacity, d.N, d.data_dim = self.capacity, self.N, self.data_dim
         d.format, d.basis_dim = self.data_format.format, self.data_format.basis_dim
@@ -212,7 +243,14 @@ class N3Tree:
         d.use_ndc = int(self.use_ndc)
         d.ndc_width, d.ndc_height, d.ndc_focal = self.ndc_width, self.ndc_height, self.ndc_focal
         h = C.c_void_p()
-        check(lib().vr_tree_create(C.byref(d), C.byref(h)))
+        if use_quant:
+            q = self.quant_
+            qd.quant_colors, qd.quant_map, qd.sigma = q["colors"].ctypes.data, q["map"].ctypes.data, q["sigma"].ctypes.data
+            qd.data_retained = q["retained"].ctypes.data if q["retained"] is not None else None
+            qd.n_quant, qd.n_retain = q["n_quant"], q["n_retain"]
+            check(lib().vr_tree_create_quantized(C.byref(qd), C.byref(h)))
+        else:
+            check(lib().vr_tree_create(C.byref(d), C.byref(h)))
         self._handle = h
         self._cuda_loaded = True
 

@@ -395,3 +395,28 @@ def c2w_to_colmajor12(c2w: np.ndarray) -> np.ndarray:
     back, centre), i.e. what ``Camera::transform`` holds (camera.cpp:52-55)."""
     m = np.asarray(c2w, np.float32)[:3, :4]
     return np.ascontiguousarray(m.T).reshape(12).copy()
+
+
+def quantise_tree(st: SynthTree, n_retain: int = 1, seed: int = 0) -> dict:
+    """A compressed (scripts/compress_octree.py:93-118 schema) version of ``st``: geometry and sigma
+    are kept, the colour coefficients come from random 65536-entry codebooks (one per quantised basis
+    function) plus ``n_retain`` un-quantised leading basis functions.  Returns the npz dict; its
+    decode (src/n3tree.cpp:279-340) defines the tree's colours."""
+    fmt = st.data_format.rstrip("0123456789")
+    if fmt == "RGBA":
+        raise ValueError("RGBA trees are not quantised")
+    n_total = (st.data_dim - 1) // 3
+    n_quant = n_total - n_retain
+    assert n_quant >= 1
+    rng = np.random.default_rng(seed)
+    cap = st.capacity
+    colors = (rng.standard_normal((n_quant, 65536, 3), dtype=np.float32) * 0.8).astype(np.float16)
+    qmap = rng.integers(0, 65536, (n_quant, cap, 2, 2, 2), dtype=np.int64).astype(np.uint16)
+    npz = dict(data_dim=np.int64(st.data_dim), data_format=np.array(st.data_format),
+               invradius3=st.invradius3.astype(np.float32), offset=st.offset.astype(np.float32), child=st.child,
+               quant_colors=colors, quant_map=qmap, sigma=np.ascontiguousarray(st.data[..., st.data_dim - 1]))
+    if n_retain > 0:
+        npz["data_retained"] = (rng.standard_normal((n_retain, cap, 2, 2, 2, 3), dtype=np.float32) * 1.2).astype(np.float16)
+    if st.extra is not None:
+        npz["extra_data"] = st.extra.astype(np.float32)
+    return npz
