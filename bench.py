@@ -124,7 +124,7 @@ def cpu_baseline(st, poses, budget_s: float = 12.0):
         counters.append(((n * 37) % len(poses), c))
         n += 1
         el = time.perf_counter() - t0
-        if el > budget_s or n >= 16:
+        if el > budget_s or n >= 400:
             break
     return {"value": W * H * n / el / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
             "sample": f"{n} full 800x800 frames of the workload, oracle/march_oracle.c with {cores} threads, {el:.1f} s"}, counters
