@@ -26,7 +26,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<int> g_variant{0};
 std::atomic<unsigned long long> g_launches{0};
-constexpr int kDefaultVariant = 19;  // persistent warps + cache-policy hints (kind 3, tune 1)
+constexpr int kDefaultVariant = 3 + 16 * 65;  // persistent warps (kind 3) + cache-policy hints (1) + wide tables (64)
 constexpr int kQueueSlots = 256;
 constexpr int kCamRing = 8192;  // device ring of per-view cameras for batched launches
 
@@ -64,6 +64,9 @@ struct vr_tree {
     uint32_t* nodes = nullptr;
     unsigned char* recs = nullptr;
     uint32_t* top = nullptr;
+    uint32_t* wide = nullptr;
+    uint32_t* wslot = nullptr;
+    long long n_tables = 0;
     float* extra = nullptr;
     unsigned int* queues = nullptr;  // kQueueSlots x {head, done}
     CamDev* cam_ring = nullptr;      // kCamRing entries; batches take consecutive slots
@@ -236,6 +239,38 @@ __global__ void build_top_kernel(const uint32_t* __restrict__ nodes, uint32_t* _
     top[cell] = node;
 }
 
+// wide[table*64 + e]: e = (ex<<4)|(ey<<2)|ez, two octree levels per axis (high bit first level).
+__global__ void build_wide_kernel(const uint32_t* __restrict__ nodes, const int* __restrict__ depth,
+                                  const uint32_t* __restrict__ tid, uint32_t* __restrict__ wide,
+                                  uint32_t* __restrict__ wslot, long long capacity) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = g >> 6;
+    const int e = (int)(g & 63);
+    if (n >= capacity) return;
+    const int d = depth[n];
+    if (d < 0 || (d & 1)) return;            // unreachable node, or odd depth: folded into its parent's table
+    const uint32_t ex = (e >> 4) & 3, ey = (e >> 2) & 3, ez = e & 3;
+    const uint32_t oct1 = ((ex >> 1) << 2) | ((ey >> 1) << 1) | (ez >> 1);
+    const size_t o = (size_t)tid[n] * 64 + e;
+    const uint32_t s1 = (uint32_t)n * 8u + oct1;
+    const uint32_t w1 = nodes[s1];
+    if (w1 & kLeafBit) {
+        wide[o] = kLeafBit | kShallowBit | (w1 & 0xffffu);
+        wslot[o] = s1;
+        return;
+    }
+    const uint32_t oct2 = ((ex & 1) << 2) | ((ey & 1) << 1) | (ez & 1);
+    const uint32_t s2 = w1 * 8u + oct2;
+    const uint32_t w2 = nodes[s2];
+    if (w2 & kLeafBit) {
+        wide[o] = kLeafBit | (w2 & 0xffffu);
+        wslot[o] = s2;
+    } else {
+        wide[o] = tid[w2];
+        wslot[o] = 0;
+    }
+}
+
 __global__ void probe_kernel(TreeDev tree, float x, float y, float z, int n_out, float* __restrict__ out) {
     // retrieve_cursor_lumisphere_kernel (volrend.cu:175-191)
     float p[3] = {tree.offset[0] + tree.scale[0] * x, tree.offset[1] + tree.scale[1] * y,
@@ -291,6 +326,7 @@ void vr_tree_destroy(vr_tree* t) {
     cudaGetDevice(&prev);
     cudaSetDevice(t->device);
     cudaFree(t->nodes); cudaFree(t->recs); cudaFree(t->top); cudaFree(t->extra); cudaFree(t->queues);
+    cudaFree(t->wide); cudaFree(t->wslot);
     cudaFree(t->cam_ring);
     for (int i = 0; i < vr_tree::HostPath::kRing; ++i) {
         cudaFree(t->host.buf[i]);
@@ -410,11 +446,32 @@ static int tree_create_impl(const vr_tree_desc* d, const vr_tree_quant_desc* q, 
     }
     build_top_kernel<<<(kTopCells + TB - 1) / TB, TB>>>(t->nodes, t->top);
     VR_CUDA(cudaGetLastError());
+    {   // two-levels-per-step tables: ids = running count of even-depth internal nodes, in node order
+        std::vector<int> h_depth((size_t)d->capacity);
+        VR_CUDA(cudaMemcpy(h_depth.data(), depth, (size_t)d->capacity * sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> h_tid((size_t)d->capacity, 0u);
+        uint32_t n_tab = 0;
+        for (long long n = 0; n < d->capacity; ++n)
+            if (h_depth[(size_t)n] >= 0 && !(h_depth[(size_t)n] & 1)) h_tid[(size_t)n] = n_tab++;
+        if (n_tab >= (1u << 30)) return fail(VR_EUNSUPPORTED, "too many nodes for the wide tables");
+        uint32_t* d_tid = nullptr;
+        struct T2 { uint32_t*& p; ~T2() { cudaFree(p); } } t2{d_tid};
+        VR_CUDA(cudaMalloc(&d_tid, (size_t)d->capacity * 4));
+        VR_CUDA(cudaMemcpy(d_tid, h_tid.data(), (size_t)d->capacity * 4, cudaMemcpyHostToDevice));
+        VR_CUDA(cudaMalloc(&t->wide, (size_t)n_tab * 64 * 4));
+        VR_CUDA(cudaMalloc(&t->wslot, (size_t)n_tab * 64 * 4));
+        const long long work = d->capacity * 64;
+        build_wide_kernel<<<(unsigned)((work + TB - 1) / TB), TB>>>(t->nodes, depth, d_tid, t->wide, t->wslot, d->capacity);
+        VR_CUDA(cudaGetLastError());
+        VR_CUDA(cudaDeviceSynchronize());
+        t->n_tables = n_tab;
+    }
     VR_CUDA(cudaDeviceSynchronize());
-    g_launches += 4;
+    g_launches += 5;
 
     TreeDev& D = t->dev;
     D.nodes = t->nodes; D.recs = t->recs; D.top = t->top; D.extra = t->extra;
+    D.wide = t->wide; D.wslot = t->wslot;
     for (int i = 0; i < 3; ++i) { D.offset[i] = d->offset[i]; D.scale[i] = d->scale[i]; }
     D.ndc_width = d->use_ndc ? d->ndc_width : -1.f;  // data_spec.hpp:47
     D.ndc_height = d->ndc_height; D.ndc_focal = d->ndc_focal;
