@@ -16,7 +16,7 @@ from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
-VARIANTS = [1, 2, 3, 4, 5, 6, 19, 3 + 16 * 64, 3 + 16 * 65]
+VARIANTS = [1, 2, 3, 4, 5, 6, 19, 3 + 16 * 64, 3 + 16 * 65, 3 + 16 * 193]
 
 
 def _torch():

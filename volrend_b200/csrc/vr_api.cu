@@ -26,7 +26,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<int> g_variant{0};
 std::atomic<unsigned long long> g_launches{0};
-constexpr int kDefaultVariant = 3 + 16 * 65;  // persistent warps (kind 3) + cache-policy hints (1) + wide tables (64)
+constexpr int kDefaultVariant = 3 + 16 * 193;  // persistent warps (kind 3) + cache hints (1) + wide tables (64) + wide-indexed records (128)
 constexpr int kQueueSlots = 256;
 constexpr int kCamRing = 8192;  // device ring of per-view cameras for batched launches
 
@@ -66,6 +66,7 @@ struct vr_tree {
     uint32_t* top = nullptr;
     uint32_t* wide = nullptr;
     uint32_t* wslot = nullptr;
+    unsigned char* wrecs = nullptr;
     long long n_tables = 0;
     float* extra = nullptr;
     unsigned int* queues = nullptr;  // kQueueSlots x {head, done}
@@ -271,6 +272,25 @@ __global__ void build_wide_kernel(const uint32_t* __restrict__ nodes, const int*
     }
 }
 
+// wrecs[entry] = recs[wslot[entry]] for leaf entries (16-byte chunks; 8-byte records as one chunk)
+__global__ void build_wrecs_kernel(const uint32_t* __restrict__ wide, const uint32_t* __restrict__ wslot,
+                                   const unsigned char* __restrict__ recs, unsigned char* __restrict__ wrecs,
+                                   long long n_entries, int rec_bytes) {
+    const int chunks = rec_bytes >= 16 ? rec_bytes / 16 : 1;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long e = gid / chunks;
+    const int c = (int)(gid % chunks);
+    if (e >= n_entries) return;
+    const bool leaf = (wide[e] & kLeafBit) != 0;
+    if (rec_bytes == 8) {
+        reinterpret_cast<uint2*>(wrecs)[e] = leaf ? reinterpret_cast<const uint2*>(recs)[wslot[e]] : make_uint2(0u, 0u);
+        return;
+    }
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (leaf) v = reinterpret_cast<const uint4*>(recs + (size_t)wslot[e] * rec_bytes)[c];
+    reinterpret_cast<uint4*>(wrecs + (size_t)e * rec_bytes)[c] = v;
+}
+
 __global__ void probe_kernel(TreeDev tree, float x, float y, float z, int n_out, float* __restrict__ out) {
     // retrieve_cursor_lumisphere_kernel (volrend.cu:175-191)
     float p[3] = {tree.offset[0] + tree.scale[0] * x, tree.offset[1] + tree.scale[1] * y,
@@ -326,7 +346,7 @@ void vr_tree_destroy(vr_tree* t) {
     cudaGetDevice(&prev);
     cudaSetDevice(t->device);
     cudaFree(t->nodes); cudaFree(t->recs); cudaFree(t->top); cudaFree(t->extra); cudaFree(t->queues);
-    cudaFree(t->wide); cudaFree(t->wslot);
+    cudaFree(t->wide); cudaFree(t->wslot); cudaFree(t->wrecs);
     cudaFree(t->cam_ring);
     for (int i = 0; i < vr_tree::HostPath::kRing; ++i) {
         cudaFree(t->host.buf[i]);
@@ -463,6 +483,11 @@ static int tree_create_impl(const vr_tree_desc* d, const vr_tree_quant_desc* q, 
         const long long work = d->capacity * 64;
         build_wide_kernel<<<(unsigned)((work + TB - 1) / TB), TB>>>(t->nodes, depth, d_tid, t->wide, t->wslot, d->capacity);
         VR_CUDA(cudaGetLastError());
+        const long long n_entries = (long long)n_tab * 64;
+        VR_CUDA(cudaMalloc(&t->wrecs, (size_t)n_entries * rec_bytes));
+        const long long rwork = n_entries * (rec_bytes >= 16 ? rec_bytes / 16 : 1);
+        build_wrecs_kernel<<<(unsigned)((rwork + TB - 1) / TB), TB>>>(t->wide, t->wslot, t->recs, t->wrecs, n_entries, rec_bytes);
+        VR_CUDA(cudaGetLastError());
         VR_CUDA(cudaDeviceSynchronize());
         t->n_tables = n_tab;
     }
@@ -471,7 +496,7 @@ static int tree_create_impl(const vr_tree_desc* d, const vr_tree_quant_desc* q, 
 
     TreeDev& D = t->dev;
     D.nodes = t->nodes; D.recs = t->recs; D.top = t->top; D.extra = t->extra;
-    D.wide = t->wide; D.wslot = t->wslot;
+    D.wide = t->wide; D.wslot = t->wslot; D.wrecs = t->wrecs;
     for (int i = 0; i < 3; ++i) { D.offset[i] = d->offset[i]; D.scale[i] = d->scale[i]; }
     D.ndc_width = d->use_ndc ? d->ndc_width : -1.f;  // data_spec.hpp:47
     D.ndc_height = d->ndc_height; D.ndc_focal = d->ndc_focal;

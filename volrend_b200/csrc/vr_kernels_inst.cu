@@ -102,16 +102,17 @@ cudaError_t launch_march(LaunchDev& P, const LaunchCfg& cfg) {
             case 10: return launch_persistent<KBD, false, false, kOutLinear, 10>(P, cfg);
             case 17: return launch_persistent<KBD, false, false, kOutLinear, 17>(P, cfg);
             case 65: return launch_persistent<KBD, false, false, kOutLinear, 65>(P, cfg);
+            case 193: return launch_persistent<KBD, false, false, kOutLinear, 193>(P, cfg);
             case 64: return launch_persistent<KBD, false, false, kOutLinear, 64>(P, cfg);
             case 16: return launch_persistent<KBD, false, false, kOutLinear, 16>(P, cfg);
             default: return cudaErrorInvalidValue;
         }
     }
     if (cfg.surface) {  // drop-in launch_renderer path: default kernel writing the caller's cudaArray
-        return launch_persistent<KBD, false, false, kOutSurface, 65>(P, cfg);
+        return launch_persistent<KBD, false, false, kOutSurface, 193>(P, cfg);
     }
     if (cfg.count) {  // instrumented build of the default kernel
-        return launch_persistent<KBD, false, true, kOutLinear, 65>(P, cfg);
+        return launch_persistent<KBD, false, true, kOutLinear, 193>(P, cfg);
     }
     if (deferred) {
         return top ? launch_deferred<KBD, true, false, kOutLinear>(P, cfg)

@@ -33,6 +33,7 @@ struct TreeDev {
     //   kLeafBit | kShallowBit (leaf is a direct child, depth 2j+1) | sigma
     const uint32_t* wide;
     const uint32_t* wslot;   // parallel array: the leaf's slot (node*8+oct) for record lookup
+    const unsigned char* wrecs;  // colour records re-indexed by wide entry (no wslot indirection)
     const float* extra;
     float offset[3];
     float scale[3];
