@@ -321,7 +321,7 @@ extern "C" {
 const char* vr_last_error(void) { return g_err.c_str(); }
 const char* vr_version(void) { return "volrend_b200 0.1 (sm_100a)"; }
 int vr_set_variant(int variant) {
-    if (variant < 0 || (variant & 15) > 6 || variant > 4095) return fail(VR_EINVAL, "variant must be kind 0..6 (+16*tune)");
+    if (variant < 0 || (variant & 15) > 6 || variant > 65535) return fail(VR_EINVAL, "variant must be kind 0..6 (+16*tune)");
     g_variant.store(variant);
     return VR_OK;
 }
