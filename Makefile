@@ -12,9 +12,10 @@ NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude -Ivolre
              -diag-suppress 20012
 # tuning builds: make lib VR_BLOCK=128 VR_MINB=7 SUFFIX=_b128m7  (selected at run time with VR_LIB_SUFFIX)
 VR_BLOCK  ?= 128
-VR_MINB   ?= 7
+VR_MINB   ?= 8
 SUFFIX    ?=
-NVFLAGS   += -DVR_BLOCK=$(VR_BLOCK) -DVR_MINB=$(VR_MINB)
+VR_TW     ?= 4
+NVFLAGS   += -DVR_BLOCK=$(VR_BLOCK) -DVR_MINB=$(VR_MINB) -DVR_TW=$(VR_TW)
 OBJ       := build/obj$(SUFFIX)
 KBDS      := m1 1 4 9 16 25
 KOBJS     := $(foreach k,$(KBDS),$(OBJ)/vr_kernels_$(k).o)

@@ -35,8 +35,8 @@ cudaError_t launch_persistent(LaunchDev& P, const LaunchCfg& cfg) {
         cached_ctas = resident_ctas(march_persistent_kernel<KBD, TOP, COUNT, OUT, TUNE>, smem, cfg.num_sms);
         cached_depth = P.tree.max_depth;
     }
-    P.tiles_x = (P.w + 7) / 8;
-    P.tiles_y = (P.h + 3) / 4;
+    P.tiles_x = (P.w + kTW - 1) / kTW;
+    P.tiles_y = (P.h + kTH - 1) / kTH;
     P.n_tiles = P.tiles_x * P.tiles_y * P.n_views;
     P.work_counter = cfg.queue;
     int grid = cached_ctas;
@@ -73,8 +73,8 @@ cudaError_t launch_deferred(LaunchDev& P, const LaunchCfg& cfg) {
         cached_ctas = resident_ctas(march_deferred_kernel<KBD, TOP, COUNT, OUT>, smem, cfg.num_sms);
         cached_depth = P.tree.max_depth;
     }
-    P.tiles_x = (P.w + 7) / 8;
-    P.tiles_y = (P.h + 3) / 4;
+    P.tiles_x = (P.w + kTW - 1) / kTW;
+    P.tiles_y = (P.h + kTH - 1) / kTH;
     P.n_tiles = P.tiles_x * P.tiles_y * P.n_views;
     P.work_counter = cfg.queue;
     int grid = cached_ctas;
