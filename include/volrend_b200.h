@@ -154,6 +154,14 @@ int vr_band_rows(int height, int band_h, int n_parts, int part);
 int vr_render_frames_host(const vr_tree* tree, const vr_camera* cams, int n_views,
                           const vr_options* opt, uint8_t* rgba8_host);
 
+/* Image egress (main_headless.cpp:216-222 with -o + src/imwrite.cpp:14-79): PNG files, 8-bit RGBA,
+ * compression level 0 / filter NONE like the reference, written without libpng (stored deflate
+ * blocks + CRC-32/Adler-32).  vr_render_frames_png renders, copies out and encodes n_views frames,
+ * overlapping the three stages; paths[i] receives view i. */
+int vr_write_png(const char* path, const uint8_t* rgba8_host, int width, int height);
+int vr_render_frames_png(const vr_tree* tree, const vr_camera* cams, int n_views, const vr_options* opt,
+                         const char* const* paths, int n_threads);
+
 /* Copies the (data_dim-1) coefficients of the leaf containing world point xyz into
  * out_dev as floats (retrieve_cursor_lumisphere_kernel). */
 int vr_probe_lumisphere(const vr_tree* tree, const float xyz_world[3], float* out_dev, void* stream);

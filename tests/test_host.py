@@ -142,3 +142,18 @@ def test_quantised_file_lazy_decode_equals_eager(synth_mod):
     np.testing.assert_array_equal(eager.data_[..., -1].view(np.uint16), st.data[..., -1].view(np.uint16))
     np.testing.assert_array_equal(eager.data_[..., 9 + 1].view(np.uint16),
                                   npz["data_retained"][1][..., 1].view(np.uint16))
+
+
+def test_png_writer_roundtrip(built, tmp_path):
+    """vr_write_png (level-0 PNG without libpng, src/imwrite.cpp semantics): any PNG reader must decode
+    exactly the RGBA8 bytes; sizes that exercise several 64 KB stored blocks and odd widths."""
+    from PIL import Image
+    from volrend_b200 import write_png_file
+    rng = np.random.default_rng(0)
+    for (h, w) in ((1, 1), (7, 13), (64, 64), (200, 333)):
+        img = rng.integers(0, 256, (h, w, 4)).astype(np.uint8)
+        p = str(tmp_path / f"t_{h}x{w}.png")
+        assert write_png_file(p, img)
+        back = np.asarray(Image.open(p))
+        assert back.shape == (h, w, 4) and np.array_equal(back, img)
+    assert not write_png_file(str(tmp_path / "nodir" / "x.png"), np.zeros((2, 2, 4), np.uint8))

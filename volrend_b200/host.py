@@ -415,6 +415,23 @@ def render_frames_host(tree: N3Tree, cams, options: RenderOptions, host_images) 
     check(lib().vr_render_frames_host(tree._handle, arr, len(cams), C.byref(o), ptr))
 
 
+def write_png_file(filename: str, rgba8, width: int | None = None, height: int | None = None) -> bool:
+    """``internal::write_png_file`` (src/imwrite.cpp:14-79) without libpng; ``rgba8``: uint8 [H,W,4]
+    host array / CPU tensor."""
+    arr = rgba8.numpy() if hasattr(rgba8, "numpy") else np.asarray(rgba8)
+    arr = np.ascontiguousarray(arr, np.uint8)
+    h, w = (arr.shape[0], arr.shape[1]) if height is None else (height, width)
+    return lib().vr_write_png(filename.encode(), arr.ctypes.data, int(w), int(h)) == 0
+
+
+def render_frames_png(tree: N3Tree, cams, options: RenderOptions, paths, n_threads: int = 8) -> None:
+    """main_headless.cpp:208-223 with ``-o``: render every pose and write one PNG per pose."""
+    arr = _cams_array(cams)
+    o = options._as_c()
+    cp = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+    check(lib().vr_render_frames_png(tree._handle, arr, len(cams), C.byref(o), cp, int(n_threads)))
+
+
 # ---------------------------------------------------------------------------- VolumeRenderer
 class VolumeRenderer:
     """GL-free offscreen ``VolumeRenderer`` (renderer.hpp:11-42)."""
