@@ -153,10 +153,11 @@ static void precalc_basis(const orc_tree* tree, const float* dir, float* out) {
         const float xx = x * x, yy = y * y, zz = z * z;
         const float xy = x * y, yz = y * z, xz = x * z;
         const double dxy = xy, dyz = yz, dxz = xz, dx = x, dy = y, dz = z;
+        /* float sub-expressions as ptxas fuses them in the reference build (SASS of lumisphere.hpp:47-66) */
+        const float xx_yy = xx - yy;
+        const float t3xx_yy = fmaf(xx, 3.f, -yy);
+        const float xx_3yy = fmaf(yy, -3.f, xx);
         if (bd >= 25) {
-            const float xx_yy = xx - yy;
-            const float t3xx_yy = xx * 3.f - yy;
-            const float xx_3yy = fmaf(yy, -3.f, xx);
             const float z7_1 = fmaf(zz, 7.f, -1.f);
             const float z7_3 = fmaf(zz, 7.f, -3.f);
             out[16] = (float)((dxy * 2.5033429417967046) * (double)xx_yy);
@@ -167,19 +168,18 @@ static void precalc_basis(const orc_tree* tree, const float* dir, float* out) {
             out[21] = (float)((dxz * -0.6690465435572892) * (double)z7_3);
             out[22] = (float)(((double)xx_yy * 0.47308734787878004) * (double)z7_1);
             out[23] = (float)((dxz * -1.7701307697799304) * (double)xx_3yy);
-            out[24] = (float)((double)(xx * xx_3yy - yy * t3xx_yy) * 0.6258357354491761);
+            out[24] = (float)((double)fmaf(xx, xx_3yy, -(yy * t3xx_yy)) * 0.6258357354491761);
         }
         if (bd >= 16) {
-            const float yy3 = yy * 3.f;
-            const float t3xx_yy = xx * 3.f - yy;
-            const float z4 = zz * 4.f - xx - yy;
+            const float z4 = -yy + fmaf(zz, 4.f, -xx);
+            const float q = fmaf(yy, -3.f, fmaf(xx, -3.f, zz + zz));
             out[9] = (float)((dy * -0.5900435899266435) * (double)t3xx_yy);
             out[10] = (float)((dxy * 2.890611442640554) * dz);
             out[11] = (float)((dy * -0.4570457994644658) * (double)z4);
-            out[12] = (float)((dz * 0.3731763325901154) * (double)((zz + zz) - xx * 3.f - yy3));
+            out[12] = (float)((dz * 0.3731763325901154) * (double)q);
             out[13] = (float)((dx * -0.4570457994644658) * (double)z4);
-            out[14] = (float)((dz * 1.445305721320277) * (double)(xx - yy));
-            out[15] = (float)((dx * -0.5900435899266435) * (double)(xx - yy3));
+            out[14] = (float)((dz * 1.445305721320277) * (double)xx_yy);
+            out[15] = (float)((dx * -0.5900435899266435) * (double)xx_3yy);
         }
         if (bd >= 9) {
             out[4] = (float)(dxy * 1.0925484305920792);
