@@ -239,21 +239,32 @@ def main():
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
     gathered_ev = [None, None]
 
+    n_chunks = 1 if world == 1 else 4     # N > 1: gather chunk k while chunk k+1 renders
+
     def step(i):
         buf = imgs[i & 1]
         cur = torch.cuda.current_stream()
         if world > 1 and gathered_ev[i & 1] is not None:
             cur.wait_event(gathered_ev[i & 1])      # this buffer's previous gather has finished
-        render_batch(tree, cams, opt, buf)
-        if world > 1:
-            # the one collective of the path: gather finished RGBA8 frames on rank 0; it runs on
-            # its own stream so it overlaps the next step's rendering (double-buffered frames)
-            comm.wait_stream(cur)
+        if world == 1:
+            render_batch(tree, cams, opt, buf)
+            return
+        # the one collective of the path: gather finished RGBA8 frames on rank 0.  The persistent
+        # render kernel owns every SM while it runs, so the sweep is cut into a few launches and each
+        # chunk's gather (own stream) overlaps the following chunk's rendering.
+        per = (N_POSES + n_chunks - 1) // n_chunks
+        ev = None
+        for c0 in range(0, N_POSES, per):
+            c1 = min(N_POSES, c0 + per)
+            render_batch(tree, cams[c0:c1], opt, buf[c0:c1])
+            done = torch.cuda.Event()
+            done.record(cur)
+            comm.wait_event(done)
             with torch.cuda.stream(comm):
-                dist.gather(buf, gathered if rank == 0 else None, dst=0)
+                dist.gather(buf[c0:c1], [g[c0:c1] for g in gathered] if rank == 0 else None, dst=0)
                 ev = torch.cuda.Event()
                 ev.record(comm)
-            gathered_ev[i & 1] = ev
+        gathered_ev[i & 1] = ev
 
     def sync_all():
         if world > 1:
