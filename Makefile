@@ -15,7 +15,8 @@ VR_BLOCK  ?= 128
 VR_MINB   ?= 8
 SUFFIX    ?=
 VR_TW     ?= 4
-NVFLAGS   += -DVR_BLOCK=$(VR_BLOCK) -DVR_MINB=$(VR_MINB) -DVR_TW=$(VR_TW)
+EXTRA     ?=
+NVFLAGS   += -DVR_BLOCK=$(VR_BLOCK) -DVR_MINB=$(VR_MINB) -DVR_TW=$(VR_TW) $(EXTRA)
 OBJ       := build/obj$(SUFFIX)
 KBDS      := m1 1 4 9 16 25
 KOBJS     := $(foreach k,$(KBDS),$(OBJ)/vr_kernels_$(k).o)
