@@ -250,13 +250,14 @@ __global__ void build_wide_kernel(const uint32_t* __restrict__ nodes, const int*
     if (n >= capacity) return;
     const int d = depth[n];
     if (d < 0 || (d & 1)) return;            // unreachable node, or odd depth: folded into its parent's table
+    // leaf entry = kLeafBit | (103 + leaf depth) << 23 | sigma: the exponent field of the cube size (vr_march.cuh)
     const uint32_t ex = (e >> 4) & 3, ey = (e >> 2) & 3, ez = e & 3;
     const uint32_t oct1 = ((ex >> 1) << 2) | ((ey >> 1) << 1) | (ez >> 1);
     const size_t o = (size_t)tid[n] * 64 + e;
     const uint32_t s1 = (uint32_t)n * 8u + oct1;
     const uint32_t w1 = nodes[s1];
     if (w1 & kLeafBit) {
-        wide[o] = kLeafBit | kShallowBit | (w1 & 0xffffu);
+        wide[o] = kLeafBit | ((uint32_t)(103 + d + 1) << 23) | (w1 & 0xffffu);
         wslot[o] = s1;
         return;
     }
@@ -264,7 +265,7 @@ __global__ void build_wide_kernel(const uint32_t* __restrict__ nodes, const int*
     const uint32_t s2 = w1 * 8u + oct2;
     const uint32_t w2 = nodes[s2];
     if (w2 & kLeafBit) {
-        wide[o] = kLeafBit | (w2 & 0xffffu);
+        wide[o] = kLeafBit | ((uint32_t)(103 + d + 2) << 23) | (w2 & 0xffffu);
         wslot[o] = s2;
     } else {
         wide[o] = tid[w2];

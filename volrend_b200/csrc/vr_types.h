@@ -9,7 +9,6 @@ namespace vrb {
 
 // Leaf flag of a node word; the low 16 bits then hold sigma as fp16 bits.
 constexpr uint32_t kLeafBit = 0x80000000u;
-constexpr uint32_t kShallowBit = 0x40000000u;
 // Level of the dense top grid staged into shared memory (16^3 cells).
 constexpr int kTopLevel = 4;
 constexpr int kTopCells = 1 << (3 * kTopLevel);
@@ -30,7 +29,7 @@ struct TreeDev {
     const uint32_t* top;
     // two-levels-per-step view of the same octree (variant "wide"): one 64-entry table per internal
     // node of even depth; entry = table id of the grandchild, or leaf word:
-    //   kLeafBit | kShallowBit (leaf is a direct child, depth 2j+1) | sigma
+    //   kLeafBit | (103 + leaf depth) << 23 | sigma   (bits 23..30 = fp32 exponent of the cube size)
     const uint32_t* wide;
     const uint32_t* wslot;   // parallel array: the leaf's slot (node*8+oct) for record lookup
     const unsigned char* wrecs;  // colour records re-indexed by wide entry (no wslot indirection)
