@@ -29,7 +29,7 @@ cudaError_t launch_tile(const LaunchDev& P, const LaunchCfg& cfg) {
 
 template <int KBD, bool TOP, bool COUNT, int OUT, int TUNE = 0>
 cudaError_t launch_persistent(LaunchDev& P, const LaunchCfg& cfg) {
-    const size_t smem = march_smem_bytes<TOP>(P.tree.max_depth) + basis_smem_bytes<KBD>();
+    const size_t smem = march_smem_bytes<TOP, (TUNE & kTuneWide) != 0 && !TOP>(P.tree.max_depth) + basis_smem_bytes<KBD>();
     static int cached_ctas = 0, cached_depth = -1;
     if (cached_ctas == 0 || cached_depth != P.tree.max_depth) {
         cached_ctas = resident_ctas(march_persistent_kernel<KBD, TOP, COUNT, OUT, TUNE>, smem, cfg.num_sms);
