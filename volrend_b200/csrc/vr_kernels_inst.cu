@@ -38,6 +38,8 @@ cudaError_t launch_persistent(LaunchDev& P, const LaunchCfg& cfg) {
     P.tiles_x = (P.w + kTW - 1) / kTW;
     P.tiles_y = (P.h + kTH - 1) / kTH;
     P.n_tiles = P.tiles_x * P.tiles_y * P.n_views;
+    set_div((uint32_t)(P.tiles_x * P.tiles_y), P.div_view_mul, P.div_view_shift);
+    set_div((uint32_t)P.tiles_x, P.div_row_mul, P.div_row_shift);
     P.work_counter = cfg.queue;
     int grid = cached_ctas;
     const int need = (P.n_tiles + (kBlock / 32) - 1) / (kBlock / 32);
@@ -76,6 +78,8 @@ cudaError_t launch_deferred(LaunchDev& P, const LaunchCfg& cfg) {
     P.tiles_x = (P.w + kTW - 1) / kTW;
     P.tiles_y = (P.h + kTH - 1) / kTH;
     P.n_tiles = P.tiles_x * P.tiles_y * P.n_views;
+    set_div((uint32_t)(P.tiles_x * P.tiles_y), P.div_view_mul, P.div_view_shift);
+    set_div((uint32_t)P.tiles_x, P.div_row_mul, P.div_row_shift);
     P.work_counter = cfg.queue;
     int grid = cached_ctas;
     const int need = (P.n_tiles + (kBlock / 32) - 1) / (kBlock / 32);

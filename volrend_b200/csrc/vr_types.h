@@ -59,6 +59,17 @@ struct OptDev {
     int32_t render_depth;
 };
 
+// Magic numbers for n / d, exact for 0 <= n < 2^31 (d >= 1): with 2^(s-1) < d <= 2^s and
+// m = ceil(2^(31+s) / d) < 2^32, floor(n*m / 2^(31+s)) = floor(n/d) because the excess
+// n*(m*d - 2^(31+s)) / (d*2^(31+s)) stays below 1/d.
+inline void set_div(uint32_t d, uint32_t& mul, int32_t& shift) {
+    if (d <= 1) { mul = 0; shift = -1; return; }
+    int s = 0;
+    while ((1ull << s) < d) ++s;
+    mul = (uint32_t)(((1ull << (31 + s)) + d - 1) / d);
+    shift = s - 1;
+}
+
 struct LaunchDev {
     TreeDev tree;
     OptDev opt;
@@ -75,6 +86,10 @@ struct LaunchDev {
     cudaSurfaceObject_t surf, dsurf;
     int32_t composite;     // 1: read existing colour from rgba8/surf + depth limit
     int32_t tiles_x, tiles_y, n_tiles;  // persistent kernels: work decomposition
+    // division of a tile index (< 2^31) by tiles_x*tiles_y and by tiles_x as multiply-high + shift
+    // (set_div): q = shift < 0 ? n : umulhi(n, mul) >> shift
+    uint32_t div_view_mul, div_row_mul;
+    int32_t div_view_shift, div_row_shift;
     unsigned int* work_counter;         // persistent kernels: global tile queue head
     unsigned long long* trace;          // diagnostics: per work item {start ns, end ns, smid, warp}
 };
