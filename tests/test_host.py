@@ -157,3 +157,48 @@ def test_png_writer_roundtrip(built, tmp_path):
         back = np.asarray(Image.open(p))
         assert back.shape == (h, w, 4) and np.array_equal(back, img)
     assert not write_png_file(str(tmp_path / "nodir" / "x.png"), np.zeros((2, 2, 4), np.uint8))
+
+
+def test_tile_decode_magic_division(tmp_path):
+    """vr_types.h:set_div (tile index -> view / row by multiply-high + shift) against n // d,
+    compiled as a host program with g++ and the CUDA headers (no GPU needed)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_inc = "/usr/local/cuda/include"
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    src = tmp_path / "div.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <cstdint>
+#include "vr_types.h"
+static uint32_t umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+int main() {
+    uint64_t bad = 0, checked = 0;
+    uint32_t ds[] = {1, 2, 3, 5, 7, 25, 100, 200, 255, 256, 257, 4999, 5000, 20000, 65535, 65536, 65537,
+                     1048575, 1048576, 1048577, 16777215, 0x7fffffffu};
+    for (uint32_t d : ds) {
+        uint32_t mul; int32_t sh;
+        vrb::set_div(d, mul, sh);
+        auto q = [&](uint32_t n) { return sh < 0 ? n : (umulhi(n, mul) >> sh); };
+        for (uint64_t k = 0; k < 4000; ++k) {   // multiples of d and their neighbours, and a stride sweep
+            uint64_t c[] = {k * d, k * d + d - 1, k * d + 1, k * 536870u + 17u, 0x7fffffffull - k};
+            for (uint64_t n : c) {
+                if (n > 0x7fffffffull) continue;
+                ++checked;
+                if (q((uint32_t)n) != (uint32_t)(n / d)) ++bad;
+            }
+        }
+    }
+    std::printf("%llu %llu\n", (unsigned long long)checked, (unsigned long long)bad);
+    return bad != 0;
+}
+''')
+    exe = tmp_path / "div"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", cuda_inc, "-I", os.path.join(root, "include"),
+                    "-I", os.path.join(root, "volrend_b200", "csrc"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    checked, bad = (int(v) for v in out.stdout.split())
+    assert bad == 0 and checked > 100000
