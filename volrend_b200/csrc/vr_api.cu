@@ -581,6 +581,10 @@ int dispatch(const vr_tree* t, LaunchDev& P, bool count, bool surface, cudaStrea
     return VR_OK;
 }
 
+// Upper bound of the warp tiles of one view for every tile shape the kernels are built with
+// (2x16, 4x8, 8x4 pixels): the persistent kernels index tiles of a whole batch with 31 bits.
+long long tile_bound(const vr_rect& r) { return ((long long)r.w / 2 + 1) * ((long long)r.h / 4 + 1); }
+
 int check_common(const vr_tree* t, const vr_camera* cam, const vr_options* opt, const vr_rect* tile, vr_rect& r) {
     if (!t || !cam || !opt) return fail(VR_EINVAL, "null argument");
     if (cam->width <= 0 || cam->height <= 0) return fail(VR_EINVAL, "bad camera size %dx%d", cam->width, cam->height);
@@ -591,6 +595,8 @@ int check_common(const vr_tree* t, const vr_camera* cam, const vr_options* opt, 
     } else {
         r.x0 = r.y0 = 0; r.w = cam->width; r.h = cam->height;
     }
+    if (tile_bound(r) > 0x7fffffffLL)
+        return fail(VR_EUNSUPPORTED, "%dx%d pixels: more tiles than the 31-bit work queue can index", r.w, r.h);
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess) return fail(VR_ENODEVICE, "no CUDA device");
     if (dev != t->device) return fail(VR_EINVAL, "tree lives on device %d but device %d is current", t->device, dev);
@@ -621,10 +627,12 @@ int vr_render_batch(const vr_tree* t, const vr_camera* cams, int n_views, const 
     P.x0 = r.x0; P.y0 = r.y0; P.w = r.w; P.h = r.h;
     P.rgba8 = rgba8_dev; P.rgbaf = reinterpret_cast<float4*>(rgba32f_dev);
     P.counters = counters_dev;
-    if (n_views > kCamRing) {  // split very large batches so each fits the camera ring
+    int max_views = kCamRing;  // split very large batches: camera ring size, 31-bit tile index
+    if (tile_bound(r) * max_views > 0x7fffffffLL) max_views = (int)(0x7fffffffLL / tile_bound(r));
+    if (n_views > max_views) {
         const size_t tile_px = (size_t)r.w * r.h;
-        for (int v0 = 0; v0 < n_views; v0 += kCamRing) {
-            const int nv = n_views - v0 < kCamRing ? n_views - v0 : kCamRing;
+        for (int v0 = 0; v0 < n_views; v0 += max_views) {
+            const int nv = n_views - v0 < max_views ? n_views - v0 : max_views;
             rc = vr_render_batch(t, cams + v0, nv, opt, tile, rgba8_dev ? rgba8_dev + 4 * tile_px * v0 : nullptr,
                                  rgba32f_dev ? rgba32f_dev + 4 * tile_px * v0 : nullptr, counters_dev, stream_);
             if (rc) return rc;
