@@ -33,6 +33,7 @@
 #ifndef VOLREND_B200_H_
 #define VOLREND_B200_H_
 #include <stddef.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -95,7 +96,13 @@ typedef struct {
     int64_t capacity;
     int32_t max_depth;               /* deepest leaf (root children = 1) */
     int32_t rec_bytes;               /* padded leaf-record stride */
-    int64_t node_bytes, rec_total_bytes, top_bytes;
+    int64_t node_bytes, rec_total_bytes, top_bytes; /* slot-indexed layout (resident in -DVR_EXPERIMENTS builds only) */
+    int32_t kernel_basis;            /* -1 RGBA, 1, 4, 9, 16, 25 */
+    int32_t wide_parity;             /* 0/1: depth parity of the nodes that own a 64-entry table */
+    int64_t n_tables;
+    int64_t wide_bytes, wrecs_bytes; /* 64-entry tables; colour records indexed by table entry */
+    int64_t kernel_bytes;            /* what the march kernels can touch: wide_bytes + wrecs_bytes */
+    int64_t device_bytes;            /* everything the tree keeps resident */
 } vr_tree_info;
 
 /* Compressed N3Tree as written by scripts/compress_octree.py:93-118 (keys quant_colors, quant_map,
@@ -162,8 +169,8 @@ int vr_write_png(const char* path, const uint8_t* rgba8_host, int width, int hei
 int vr_render_frames_png(const vr_tree* tree, const vr_camera* cams, int n_views, const vr_options* opt,
                          const char* const* paths, int n_threads);
 
-/* Copies the (data_dim-1) coefficients of the leaf containing world point xyz into
- * out_dev as floats (retrieve_cursor_lumisphere_kernel). */
+/* Copies the colour coefficients of the leaf containing world point xyz into out_dev as floats
+ * (retrieve_cursor_lumisphere_kernel): min(data_dim-1, 3*basis_dim) values (3 for RGBA). */
 int vr_probe_lumisphere(const vr_tree* tree, const float xyz_world[3], float* out_dev, void* stream);
 
 /* Diagnostics: one full-frame render with the instrumented kernel that also records, per 8x4-pixel
@@ -172,9 +179,30 @@ int vr_probe_lumisphere(const vr_tree* tree, const float xyz_world[3], float* ou
 int vr_debug_trace(const vr_tree* tree, const vr_camera* cam, const vr_options* opt, uint8_t* rgba8_dev,
                    vr_counters* counters_dev, unsigned long long* trace_dev, void* stream);
 
-/* Kernel variant selection for measurement (0 = default/best). */
+/* Kernel variant selection for measurement.  0 = default: the shading-queue kernel (7) for trees with
+ * >= 4 basis functions, the inline-shading kernel (3 + 16*193) otherwise.  vr_get_variant returns the
+ * process-wide setting (0 unless changed), vr_tree_variant the variant a launch on `tree` resolves to
+ * (-1 if the setting is not available for its basis size), vr_variant_supported whether `variant`
+ * is built into this library for a kernel basis of -1 (RGBA), 1, 4, 9, 16 or 25. */
 int vr_set_variant(int variant);
 int vr_get_variant(void);
+int vr_tree_variant(const vr_tree* tree);
+int vr_variant_supported(int kernel_basis, int variant);
+/* Cap the grid of the persistent march kernels at `max_ctas` CTAs (0 = all resident CTAs).  Used by
+ * multi-GPU drivers to leave a few SMs to a concurrently running peer copy. */
+int vr_set_max_ctas(int max_ctas);
+/* Multi-GPU plumbing without SM-resident collectives: finished RGBA8 frames / bands are moved to the
+ * gathering GPU by the copy engines over NVLink (cudaMemcpyAsync between peer-mapped buffers), so the
+ * persistent march kernel keeps every SM.  vr_dev_alloc returns plain cudaMalloc memory (the base
+ * address an IPC handle needs); vr_ipc_export writes the 64-byte cudaIpcMemHandle_t of such a buffer,
+ * vr_ipc_open maps a peer process's buffer into this process (enabling peer access when possible),
+ * vr_copy_async is a stream-ordered device/peer/host copy (kind inferred from the pointers). */
+int vr_dev_alloc(size_t bytes, void** ptr);
+int vr_dev_free(void* ptr);
+int vr_ipc_export(void* dev_ptr, unsigned char handle_out[64]);
+int vr_ipc_open(const unsigned char handle[64], void** ptr_out);
+int vr_ipc_close(void* ptr);
+int vr_copy_async(void* dst, const void* src, size_t bytes, void* stream);
 /* How many of this library's kernels were launched by this process. */
 unsigned long long vr_launch_count(void);
 

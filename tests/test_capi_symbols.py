@@ -33,8 +33,16 @@ def test_version_and_variant(built):
     assert b"sm_100a" in l.vr_version()
     assert l.vr_set_variant(9) != 0 and b"variant" in l.vr_last_error()
     assert l.vr_set_variant(300) != 0
-    assert l.vr_set_variant(0) == 0
-    assert 1 <= (l.vr_get_variant() & 15) <= 6
+    assert l.vr_set_variant(-1) != 0
+    assert l.vr_set_variant(0) == 0 and l.vr_get_variant() == 0
+    # product kernels: shading queue (7) for >= 4 basis functions, inline shading (3 + 16*193) for every basis size
+    for kbd in (4, 9, 16, 25):
+        assert l.vr_variant_supported(kbd, 7) == 1 and l.vr_variant_supported(kbd, 3 + 16 * 193) == 1
+    for kbd in (-1, 1):
+        assert l.vr_variant_supported(kbd, 7) == 0 and l.vr_variant_supported(kbd, 3 + 16 * 193) == 1
+    assert l.vr_variant_supported(16, 0) == 1 and l.vr_variant_supported(5, 0) == 0
+    assert l.vr_set_variant(7) == 0 and l.vr_get_variant() == 7 and l.vr_set_variant(0) == 0
+    assert l.vr_set_max_ctas(-1) != 0 and l.vr_set_max_ctas(0) == 0
 
 
 def test_default_options_match_reference_defaults(built):

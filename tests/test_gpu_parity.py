@@ -16,7 +16,14 @@ from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
-VARIANTS = [1, 2, 3, 4, 5, 6, 19, 3 + 16 * 64, 3 + 16 * 65, 3 + 16 * 193]
+QUEUE, INLINE = 7, 3 + 16 * 193     # the two product kernels (vr_kernels.h)
+# round-1 experiment kernels: present only in a -DVR_EXPERIMENTS build (make lib EXTRA=-DVR_EXPERIMENTS)
+VARIANTS = [QUEUE, INLINE, 1, 2, 3, 4, 5, 6, 19, 3 + 16 * 64, 3 + 16 * 65]
+
+
+def supported(tree, variant) -> bool:
+    from volrend_b200 import lib
+    return bool(lib().vr_variant_supported(tree.info()["kernel_basis"], variant))
 
 
 def _torch():
@@ -71,9 +78,11 @@ def dev_trees(small_trees):
 def test_matches_oracle_all_formats(built, dev_trees, name, variant):
     from volrend_b200 import RenderOptions, synth
     st, tree = dev_trees[name]
+    if not supported(tree, variant):
+        pytest.skip("variant not built for this basis size (experiments need -DVR_EXPERIMENTS)")
     pose = synth.config1_pose() if name == "sh1_full4" else synth.nerf_synthetic_test_poses(8)[(len(name) * 3) % 8]
     cam = make_cam(72, 56, pose)
-    f, u, cnt = gpu_render(tree, cam, RenderOptions(), variant=variant, counters=(variant >= 5))   # counters always come from the instrumented default kernel
+    f, u, cnt = gpu_render(tree, cam, RenderOptions(), variant=variant, counters=(variant in (QUEUE, INLINE, 5, 6)))   # instrumented builds of the two product kernels
     fo, uo, co = oracle_render(st, cam, {})
     assert np.abs(f - fo).max() <= TOL
     assert np.abs(f - fo).max() <= 2e-6          # what we actually achieve (expf ulps only)
@@ -168,8 +177,10 @@ def test_tiles_batches_and_variants_are_bit_identical(built, dev_trees):
     poses = synth.nerf_synthetic_test_poses(8)
     cams = [make_cam(100, 76, p) for p in poses[:5]]
     opt = RenderOptions()
-    full = [gpu_render(tree, c, opt, variant=1) for c in cams]
-    for v in VARIANTS[1:]:
+    full = [gpu_render(tree, c, opt, variant=INLINE) for c in cams]
+    for v in VARIANTS:
+        if not supported(tree, v):
+            continue
         f, u, _ = gpu_render(tree, cams[0], opt, variant=v)
         assert np.array_equal(f, full[0][0]) and np.array_equal(u, full[0][1]), v
     for tile in [(0, 0, 100, 76), (13, 7, 50, 33), (96, 70, 4, 6), (0, 38, 100, 38), (5, 5, 1, 1)]:
@@ -177,7 +188,9 @@ def test_tiles_batches_and_variants_are_bit_identical(built, dev_trees):
         x0, y0, w, h = tile
         assert np.array_equal(ft, full[1][0][y0:y0 + h, x0:x0 + w]), tile
         assert np.array_equal(ut, full[1][1][y0:y0 + h, x0:x0 + w]), tile
-    for v in (1, 3, 5):
+    for v in (QUEUE, INLINE, 1, 5):
+        if not supported(tree, v):
+            continue
         lib().vr_set_variant(v)
         imgs = torch.zeros((len(cams), 76, 100, 4), dtype=torch.uint8, device="cuda")
         fo = torch.zeros((len(cams), 76, 100, 4), dtype=torch.float32, device="cuda")
@@ -285,7 +298,7 @@ def test_full_size_properties(built):
     cams = [make_cam(800, 800, p) for p in poses]
     opt = RenderOptions()
     outs = {}
-    for v in (1, 5):
+    for v in (QUEUE, INLINE):
         lib().vr_set_variant(v)
         imgs = torch.zeros((len(cams), 800, 800, 4), dtype=torch.uint8, device="cuda")
         fo = torch.zeros((len(cams), 800, 800, 4), dtype=torch.float32, device="cuda")
@@ -295,8 +308,9 @@ def test_full_size_properties(built):
         torch.cuda.synchronize()
         outs[v] = (fo.cpu().numpy(), imgs.cpu().numpy(), cnt.cpu().tolist())
     lib().vr_set_variant(0)
-    f, u, cnt = outs[5]
-    assert np.array_equal(f, outs[1][0]) and np.array_equal(u, outs[1][1])     # variant-independent
+    f, u, cnt = outs[QUEUE]
+    assert np.array_equal(f, outs[INLINE][0]) and np.array_equal(u, outs[INLINE][1])     # variant-independent
+    assert cnt == outs[INLINE][2]
     assert np.isfinite(f).all() and f[..., 3].min() >= 0 and f[..., 3].max() <= 1
     assert (f[..., :3] >= 0).all() and (f[..., :3] <= 1 + 1e-5).all()         # sigmoid colours, bg <= 1
     assert np.all(u[..., 3] == 255)

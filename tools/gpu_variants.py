@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Variant sweep for one gpurun call: bit-exactness of every kernel variant against variant 1 on a
+"""Variant sweep for one gpurun call: bit-exactness of every kernel variant against the inline-shading kernel on a
 small tree, then batch (200 views / launch) and per-frame (1 view / launch, C-ABI called with
 prebuilt structs) timings on the bench tree.  usage: gpu_variants.py v1,v2,... [depth]"""
 import ctypes as C
@@ -15,7 +15,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from volrend_b200 import synth, N3Tree, Camera, RenderOptions, launch_renderer, render_batch, render_frames_host, lib  # noqa: E402
 from volrend_b200 import _capi  # noqa: E402
 
-variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "1,3,4,5,6").split(",")]
+variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "7").split(",")]
+INLINE = 3 + 16 * 193
 depth = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 dev = torch.device("cuda:0")
 res = {}
@@ -26,7 +27,7 @@ tree = N3Tree.from_synth(st)
 cam = Camera(256, 200, synth.focal_for(256), synth.focal_for(256))
 cam.set_c2w(synth.nerf_synthetic_test_poses(8)[3])
 ref = None
-for v in [1] + variants:
+for v in [INLINE] + variants:
     assert lib().vr_set_variant(v) == 0, v
     fo = torch.zeros((200, 256, 4), dtype=torch.float32, device=dev)
     img = torch.zeros((200, 256, 4), dtype=torch.uint8, device=dev)
@@ -37,8 +38,8 @@ for v in [1] + variants:
         ref = f
     else:
         ok = bool(np.array_equal(f, ref))
-        res.setdefault("bit_exact_vs_v1", {})[v] = ok
-        print("variant", v, "bit-exact vs v1:", ok, flush=True)
+        res.setdefault("bit_exact_vs_inline", {})[v] = ok
+        print("variant", v, "bit-exact vs inline-shading kernel:", ok, flush=True)
 del tree
 
 # ---- timing

@@ -53,7 +53,10 @@ class vr_counters(C.Structure):
 
 class vr_tree_info(C.Structure):
     _fields_ = [("capacity", C.c_int64), ("max_depth", C.c_int32), ("rec_bytes", C.c_int32),
-                ("node_bytes", C.c_int64), ("rec_total_bytes", C.c_int64), ("top_bytes", C.c_int64)]
+                ("node_bytes", C.c_int64), ("rec_total_bytes", C.c_int64), ("top_bytes", C.c_int64),
+                ("kernel_basis", C.c_int32), ("wide_parity", C.c_int32), ("n_tables", C.c_int64),
+                ("wide_bytes", C.c_int64), ("wrecs_bytes", C.c_int64), ("kernel_bytes", C.c_int64),
+                ("device_bytes", C.c_int64)]
 
 
 # name -> (restype, argtypes); every symbol include/volrend_b200.h declares
@@ -84,6 +87,15 @@ SYMBOLS = {
                                  C.c_void_p, C.c_void_p]),
     "vr_set_variant": (C.c_int, [C.c_int]),
     "vr_get_variant": (C.c_int, []),
+    "vr_tree_variant": (C.c_int, [C.c_void_p]),
+    "vr_variant_supported": (C.c_int, [C.c_int, C.c_int]),
+    "vr_set_max_ctas": (C.c_int, [C.c_int]),
+    "vr_dev_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "vr_dev_free": (C.c_int, [C.c_void_p]),
+    "vr_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "vr_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "vr_ipc_close": (C.c_int, [C.c_void_p]),
+    "vr_copy_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "vr_launch_count": (C.c_ulonglong, []),
     "vr_last_error": (C.c_char_p, []),
     "vr_version": (C.c_char_p, []),

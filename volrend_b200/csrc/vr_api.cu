@@ -6,6 +6,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cub/device/device_scan.cuh>
+
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -13,6 +15,8 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "volrend_b200.h"
@@ -26,7 +30,9 @@ namespace {
 thread_local std::string g_err;
 std::atomic<int> g_variant{0};
 std::atomic<unsigned long long> g_launches{0};
-constexpr int kDefaultVariant = 3 + 16 * 193;  // persistent warps (kind 3) + cache hints (1) + wide tables (64) + wide-indexed records (128)
+std::atomic<int> g_max_ctas{0};
+// Resolved default variants (vr_kernels.h): queue kernel for >= 4 basis functions, else inline shading
+constexpr int kVariantQueue = 7, kVariantInline = 3 + 16 * 193;
 constexpr int kQueueSlots = 256;
 constexpr int kCamRing = 8192;  // device ring of per-view cameras for batched launches
 
@@ -57,22 +63,30 @@ int kernel_basis(int format, int basis_dim) {
 int rec_bytes_for(int kbd) { return kbd <= 1 ? 8 : ((3 * kbd * 2 + 15) / 16) * 16; }
 }  // namespace
 
+// Per-stream launch resources of a tree.  Work-queue slots and the camera ring are recycled in
+// stream order only: a launch that reuses a slot is ordered behind the launch that used it before, so
+// no fence is needed, and launches on different streams never share a slot.
+struct StreamRes {
+    unsigned int* queues = nullptr;  // kQueueSlots x {head, done}
+    CamDev* cam_ring = nullptr;      // kCamRing entries; batches take consecutive slots
+    unsigned int next_queue = 0, cam_pos = 0;
+};
+
 struct vr_tree {
     int device = 0;
     int num_sms = 0;
     TreeDev dev{};
+    uint32_t* wide = nullptr;
+    unsigned char* wrecs = nullptr;
+    float* extra = nullptr;
+    // slot-indexed arrays: only the experiment kernels (-DVR_EXPERIMENTS) read them
     uint32_t* nodes = nullptr;
     unsigned char* recs = nullptr;
     uint32_t* top = nullptr;
-    uint32_t* wide = nullptr;
     uint32_t* wslot = nullptr;
-    unsigned char* wrecs = nullptr;
     long long n_tables = 0;
-    float* extra = nullptr;
-    unsigned int* queues = nullptr;  // kQueueSlots x {head, done}
-    CamDev* cam_ring = nullptr;      // kCamRing entries; batches take consecutive slots
-    std::mutex cam_mu;
-    unsigned int cam_pos = 0;
+    std::mutex res_mu;
+    std::unordered_map<cudaStream_t, StreamRes> res;
     // vr_render_frames_host: chunk ring, streams and events are created once and kept
     struct HostPath {
         static constexpr int kRing = 4;
@@ -83,75 +97,119 @@ struct vr_tree {
         bool ready = false;
     } host;
     std::mutex host_mu;
-    std::atomic<unsigned int> next_queue{0};
     vr_tree_info info{};
     int data_dim = 0;
-    size_t l2_window_bytes = 0;  // node-table window kept in persisting L2 (VR_L2_PERSIST=1)
+    size_t l2_window_bytes = 0;  // table window kept in persisting L2 (VR_L2_PERSIST=1)
 };
+
+// ------------------------------------------------------------------------------------ upload
+namespace {
+
+// Host -> device copy of a large pageable array at pinned-memory speed: a few worker threads copy
+// chunks into process-wide pinned staging buffers and issue the DMA from there (the reference uploads
+// with one synchronous pageable cudaMemcpy, src/cuda/n3tree.cu:20-33, ~12 GB/s).
+class Uploader {
+  public:
+    static constexpr int kWorkers = 4;
+    static constexpr size_t kChunk = 8u << 20;
+    static Uploader& get() { static Uploader u; return u; }
+    cudaError_t copy(void* dst, const void* src, size_t bytes) {
+        if (bytes < 4 * kChunk || !ensure()) return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+        std::lock_guard<std::mutex> lk(mu_);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const size_t n_chunks = (bytes + kChunk - 1) / kChunk;
+        std::atomic<int> err{0};
+        std::vector<std::thread> th;
+        for (int w = 0; w < kWorkers; ++w)
+            th.emplace_back([&, w]() {
+                cudaSetDevice(dev);
+                cudaStream_t st = nullptr;
+                cudaEvent_t ev[2] = {nullptr, nullptr};
+                if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { err = 1; return; }
+                for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+                int k = 0;
+                for (size_t c = (size_t)w; c < n_chunks && !err; c += kWorkers, ++k) {
+                    const size_t off = c * kChunk, n = bytes - off < kChunk ? bytes - off : kChunk;
+                    unsigned char* stage = stage_[2 * w + (k & 1)];
+                    if (k >= 2) cudaEventSynchronize(ev[k & 1]);   // the DMA that last read this buffer is done
+                    memcpy(stage, (const unsigned char*)src + off, n);
+                    if (cudaMemcpyAsync((unsigned char*)dst + off, stage, n, cudaMemcpyHostToDevice, st) != cudaSuccess) err = 1;
+                    cudaEventRecord(ev[k & 1], st);
+                }
+                if (cudaStreamSynchronize(st) != cudaSuccess) err = 1;
+                for (auto& e : ev) cudaEventDestroy(e);
+                cudaStreamDestroy(st);
+            });
+        for (auto& t : th) t.join();
+        return err ? cudaErrorUnknown : cudaSuccess;
+    }
+
+  private:
+    bool ensure() {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (ready_) return true;
+        if (failed_) return false;
+        for (int i = 0; i < 2 * kWorkers; ++i)
+            if (cudaHostAlloc((void**)&stage_[i], kChunk, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                failed_ = true;
+                return false;
+            }
+        ready_ = true;
+        return true;
+    }
+    std::mutex mu_;
+    unsigned char* stage_[2 * kWorkers] = {};
+    bool ready_ = false, failed_ = false;
+};
+
+}  // namespace
 
 // ------------------------------------------------------------------------------------ re-layout kernels
 namespace {
 
-// nodes[i]: absolute child id, or leaf bit | sigma.  Also validates child links.
-__global__ void relayout_nodes_kernel(const int32_t* __restrict__ child, const unsigned short* __restrict__ data,
-                                      uint32_t* __restrict__ nodes, long long n_slots, long long capacity,
-                                      int data_dim, int* __restrict__ bad) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
-    const int32_t rel = child[i];
-    if (rel != 0) {
-        const long long tgt = (i >> 3) + rel;
-        if (tgt <= 0 || tgt >= capacity) {
-            atomicExch(bad, 1);
-            nodes[i] = kLeafBit;
-        } else {
-            nodes[i] = (uint32_t)tgt;
-        }
-    } else {
-        nodes[i] = kLeafBit | (uint32_t)data[(size_t)i * data_dim + (data_dim - 1)];
-    }
-}
-
-// recs[i]: colour coefficients of slot i, padded.  One thread per (slot, 16-byte chunk).
-__global__ void relayout_recs_kernel(const unsigned short* __restrict__ data, unsigned char* __restrict__ recs,
-                                     long long n_slots, int data_dim, int basis_dim, int kbd, int rec_bytes) {
-    const int chunks = rec_bytes >= 16 ? rec_bytes / 16 : 1;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long slot = gid / chunks;
-    const int chunk = (int)(gid % chunks);
-    if (slot >= n_slots) return;
-    const unsigned short* src = data + (size_t)slot * data_dim;
-    if (rec_bytes == 8) {
-        // one coefficient per channel: RGBA -> halfs 0,1,2 ; basis -> k[0], k[bd], k[2bd]
-        const int stride = kbd < 0 ? 1 : basis_dim;
-        ushort4 v;
-        v.x = src[0]; v.y = src[stride]; v.z = src[2 * stride]; v.w = 0;
-        reinterpret_cast<ushort4*>(recs)[slot] = v;
-        return;
-    }
-    const int n_coef = 3 * kbd;
-    unsigned short h[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = chunk * 8 + j;
-        h[j] = c < n_coef ? src[c] : (unsigned short)0;
-    }
-    uint4 v;
-    v.x = h[0] | ((uint32_t)h[1] << 16); v.y = h[2] | ((uint32_t)h[3] << 16);
-    v.z = h[4] | ((uint32_t)h[5] << 16); v.w = h[6] | ((uint32_t)h[7] << 16);
-    reinterpret_cast<uint4*>(recs + (size_t)slot * rec_bytes)[chunk] = v;
-}
-
-// Quantised trees (scripts/compress_octree.py; CPU decode in src/n3tree.cpp:309-340):
+// Source of the fp16 leaf data: the plain [slot][data_dim] array, or a quantised tree
+// (scripts/compress_octree.py; CPU decode in src/n3tree.cpp:309-340):
 //   data[slot][j + n_retain + k*n_total] = quant_colors[j][quant_map[j][slot]][k]   j < n_quant
 //   data[slot][j + k*n_total]            = data_retained[j][slot][k]                j < n_retain
 //   data[slot][data_dim-1]               = sigma[slot]
-// decoded here straight into the padded records / node words.
-__global__ void quant_nodes_kernel(const int32_t* __restrict__ child, const unsigned short* __restrict__ sigma,
-                                   uint32_t* __restrict__ nodes, long long n_slots, long long capacity,
-                                   int* __restrict__ bad) {
+struct LeafSrc {
+    const unsigned short* data;      // plain
+    const unsigned short* colors;    // quantised
+    const unsigned short* qmap;
+    const unsigned short* retained;
+    const unsigned short* sigma;
+    long long n_slots;
+    int data_dim, basis_dim, kbd, n_total, n_retain;
+};
+
+__device__ __forceinline__ unsigned short leaf_sigma(const LeafSrc& S, long long slot) {
+    return S.data ? S.data[(size_t)slot * S.data_dim + (S.data_dim - 1)] : S.sigma[slot];
+}
+
+// half c (= channel * kbd + j) of the padded colour record of `slot`
+__device__ __forceinline__ unsigned short leaf_half(const LeafSrc& S, long long slot, int c) {
+    if (S.kbd <= 1) {  // one coefficient per channel: RGBA -> halfs 0,1,2 ; basis -> k[0], k[bd], k[2bd]
+        if (c >= 3) return 0;
+        if (S.data) return S.data[(size_t)slot * S.data_dim + (S.kbd < 0 ? c : c * S.basis_dim)];
+        const int j = 0, k = c;  // quantised trees are never RGBA
+        if (j < S.n_retain) return S.retained[((size_t)j * S.n_slots + slot) * 3 + k];
+        return S.colors[((size_t)(j - S.n_retain) * 65536 + S.qmap[(size_t)(j - S.n_retain) * S.n_slots + slot]) * 3 + k];
+    }
+    if (c >= 3 * S.kbd) return 0;
+    if (S.data) return S.data[(size_t)slot * S.data_dim + c];
+    const int j = c % S.n_total, k = c / S.n_total;   // kbd == n_total here
+    if (j < S.n_retain) return S.retained[((size_t)j * S.n_slots + slot) * 3 + k];
+    const int q = j - S.n_retain;
+    return S.colors[((size_t)q * 65536 + S.qmap[(size_t)q * S.n_slots + slot]) * 3 + k];
+}
+
+// nodes[i]: absolute child id, or leaf bit | sigma.  Also validates child links.
+__global__ void relayout_nodes_kernel(const int32_t* __restrict__ child, LeafSrc S, uint32_t* __restrict__ nodes,
+                                      long long capacity, int* __restrict__ bad) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
+    if (i >= S.n_slots) return;
     const int32_t rel = child[i];
     if (rel != 0) {
         const long long tgt = (i >> 3) + rel;
@@ -162,63 +220,137 @@ __global__ void quant_nodes_kernel(const int32_t* __restrict__ child, const unsi
             nodes[i] = (uint32_t)tgt;
         }
     } else {
-        nodes[i] = kLeafBit | (uint32_t)sigma[i];
+        nodes[i] = kLeafBit | (uint32_t)leaf_sigma(S, i);
     }
 }
 
-__device__ __forceinline__ unsigned short quant_coeff(const unsigned short* __restrict__ colors,
-                                                      const unsigned short* __restrict__ qmap,
-                                                      const unsigned short* __restrict__ retained, long long n_slots,
-                                                      long long slot, int n_retain, int j, int k) {
-    if (j < n_retain) return retained[((size_t)j * n_slots + slot) * 3 + k];
-    const int q = j - n_retain;
-    const unsigned int id = qmap[(size_t)q * n_slots + slot];
-    return colors[((size_t)q * 65536 + id) * 3 + k];
-}
-
-__global__ void quant_recs_kernel(const unsigned short* __restrict__ colors, const unsigned short* __restrict__ qmap,
-                                  const unsigned short* __restrict__ retained, unsigned char* __restrict__ recs,
-                                  long long n_slots, int n_total, int n_retain, int kbd, int rec_bytes) {
-    const int chunks = rec_bytes >= 16 ? rec_bytes / 16 : 1;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long slot = gid / chunks;
-    const int chunk = (int)(gid % chunks);
-    if (slot >= n_slots) return;
-    if (rec_bytes == 8) {  // one coefficient per channel (basis sizes the reference's switch ignores)
-        ushort4 v;
-        v.x = quant_coeff(colors, qmap, retained, n_slots, slot, n_retain, 0, 0);
-        v.y = quant_coeff(colors, qmap, retained, n_slots, slot, n_retain, 0, 1);
-        v.z = quant_coeff(colors, qmap, retained, n_slots, slot, n_retain, 0, 2);
-        v.w = 0;
-        reinterpret_cast<ushort4*>(recs)[slot] = v;
-        return;
-    }
-    unsigned short h[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = chunk * 8 + i;                 // record half index = k*kbd + j (kbd == n_total here)
-        h[i] = c < 3 * kbd ? quant_coeff(colors, qmap, retained, n_slots, slot, n_retain, c % n_total, c / n_total)
-                           : (unsigned short)0;
-    }
-    uint4 v;
-    v.x = h[0] | ((uint32_t)h[1] << 16); v.y = h[2] | ((uint32_t)h[3] << 16);
-    v.z = h[4] | ((uint32_t)h[5] << 16); v.w = h[6] | ((uint32_t)h[7] << 16);
-    reinterpret_cast<uint4*>(recs + (size_t)slot * rec_bytes)[chunk] = v;
-}
-
-// depth[n] of every node by level-synchronous relaxation from the root.
+// depth[n] of every node by level-synchronous relaxation from the root.  A node that is reached
+// twice (two parents, or a cycle) makes the input a DAG, not a tree: rejected, because the table
+// builder and the ancestor stacks assume one depth per node.
 __global__ void node_depth_kernel(const uint32_t* __restrict__ nodes, int* __restrict__ depth, long long capacity,
-                                  int level, int* __restrict__ changed) {
+                                  int level, int* __restrict__ flags) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= capacity || depth[n] != level) return;
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
         const uint32_t w = nodes[n * 8 + s];
         if (!(w & kLeafBit)) {
-            depth[w] = level + 1;
-            *changed = 1;
+            if (atomicCAS(&depth[w], -1, level + 1) != -1) atomicExch(flags + 2, 1);
+            flags[1] = 1;
         }
     }
+}
+
+// per parity p: number of internal nodes that would own a table
+__global__ void count_parity_kernel(const int* __restrict__ depth, long long capacity, unsigned long long* __restrict__ cnt) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int c0 = 0, c1 = 0;
+    if (n < capacity && depth[n] >= 0) { c0 = !(depth[n] & 1); c1 = depth[n] & 1; }
+    c0 = __reduce_add_sync(0xffffffffu, c0);
+    c1 = __reduce_add_sync(0xffffffffu, c1);
+    if ((threadIdx.x & 31) == 0) {
+        if (c0) atomicAdd(cnt, (unsigned long long)c0);
+        if (c1) atomicAdd(cnt + 1, (unsigned long long)c1);
+    }
+}
+
+__global__ void table_flag_kernel(const int* __restrict__ depth, long long capacity, int p, uint32_t* __restrict__ flag) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= capacity) return;
+    const int d = depth[n];
+    flag[n] = (d >= 0 && (n == 0 || ((d ^ p) & 1) == 0)) ? 1u : 0u;
+}
+
+// wide[table*64 + e]: e = (ex<<4)|(ey<<2)|ez, two octree levels per axis (high bit first level).  With
+// p = 1 the root table resolves level 1 only (entries with ex,ey,ez in {0,1}).
+__global__ void build_wide_kernel(const uint32_t* __restrict__ nodes, const int* __restrict__ depth,
+                                  const uint32_t* __restrict__ tid, uint32_t* __restrict__ wide,
+                                  uint32_t* __restrict__ wslot, long long capacity, int p) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = g >> 6;
+    const int e = (int)(g & 63);
+    if (n >= capacity) return;
+    const int d = depth[n];
+    if (d < 0 || (n != 0 && ((d ^ p) & 1))) return;   // unreachable, or folded into its parent's table
+    // leaf entry = kLeafBit | (103 + leaf depth) << 23 | sigma: the exponent field of the cube size (vr_march.cuh)
+    const uint32_t ex = (e >> 4) & 3, ey = (e >> 2) & 3, ez = e & 3;
+    const size_t o = (size_t)tid[n] * 64 + e;
+    if (n == 0 && p == 1) {   // single-level root table: entry6 with shift 23 yields 0/1 per axis
+        const uint32_t oct = ((ex & 1) << 2) | ((ey & 1) << 1) | (ez & 1);
+        const uint32_t s1 = oct, w1 = nodes[s1];
+        if (w1 & kLeafBit) { wide[o] = kLeafBit | ((uint32_t)(103 + 1) << 23) | (w1 & 0xffffu); wslot[o] = s1; }
+        else { wide[o] = tid[w1]; wslot[o] = 0xffffffffu; }
+        return;
+    }
+    const uint32_t oct1 = ((ex >> 1) << 2) | ((ey >> 1) << 1) | (ez >> 1);
+    const uint32_t s1 = (uint32_t)n * 8u + oct1;
+    const uint32_t w1 = nodes[s1];
+    if (w1 & kLeafBit) {
+        wide[o] = kLeafBit | ((uint32_t)(103 + d + 1) << 23) | (w1 & 0xffffu);
+        wslot[o] = s1;
+        return;
+    }
+    const uint32_t oct2 = ((ex & 1) << 2) | ((ey & 1) << 1) | (ez & 1);
+    const uint32_t s2 = w1 * 8u + oct2;
+    const uint32_t w2 = nodes[s2];
+    if (w2 & kLeafBit) {
+        wide[o] = kLeafBit | ((uint32_t)(103 + d + 2) << 23) | (w2 & 0xffffu);
+        wslot[o] = s2;
+    } else {
+        wide[o] = tid[w2];
+        wslot[o] = 0xffffffffu;
+    }
+}
+
+// wrecs[entry]: padded colour record of the entry's leaf, straight from the source arrays
+// (16-byte chunks; 8-byte records as one chunk).  Entries that are not leaves stay zero.
+__global__ void build_wrecs_kernel(const uint32_t* __restrict__ wslot, LeafSrc S, unsigned char* __restrict__ wrecs,
+                                   long long n_entries, int rec_bytes) {
+    const int chunks = rec_bytes >= 16 ? rec_bytes / 16 : 1;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long e = gid / chunks;
+    const int c = (int)(gid % chunks);
+    if (e >= n_entries) return;
+    const uint32_t slot = wslot[e];
+    const bool leaf = slot != 0xffffffffu;
+    if (rec_bytes == 8) {
+        ushort4 v = make_ushort4(0, 0, 0, 0);
+        if (leaf) { v.x = leaf_half(S, slot, 0); v.y = leaf_half(S, slot, 1); v.z = leaf_half(S, slot, 2); }
+        reinterpret_cast<ushort4*>(wrecs)[e] = v;
+        return;
+    }
+    unsigned short h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (leaf) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = leaf_half(S, slot, c * 8 + j);
+    }
+    uint4 v;
+    v.x = h[0] | ((uint32_t)h[1] << 16); v.y = h[2] | ((uint32_t)h[3] << 16);
+    v.z = h[4] | ((uint32_t)h[5] << 16); v.w = h[6] | ((uint32_t)h[7] << 16);
+    reinterpret_cast<uint4*>(wrecs + (size_t)e * rec_bytes)[c] = v;
+}
+
+#ifdef VR_EXPERIMENTS
+// recs[i]: colour coefficients of slot i, padded.  One thread per (slot, 16-byte chunk).
+__global__ void relayout_recs_kernel(LeafSrc S, unsigned char* __restrict__ recs, int rec_bytes) {
+    const int chunks = rec_bytes >= 16 ? rec_bytes / 16 : 1;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long slot = gid / chunks;
+    const int c = (int)(gid % chunks);
+    if (slot >= S.n_slots) return;
+    if (rec_bytes == 8) {
+        ushort4 v;
+        v.x = leaf_half(S, slot, 0); v.y = leaf_half(S, slot, 1); v.z = leaf_half(S, slot, 2); v.w = 0;
+        reinterpret_cast<ushort4*>(recs)[slot] = v;
+        return;
+    }
+    unsigned short h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = leaf_half(S, slot, c * 8 + j);
+    uint4 v;
+    v.x = h[0] | ((uint32_t)h[1] << 16); v.y = h[2] | ((uint32_t)h[3] << 16);
+    v.z = h[4] | ((uint32_t)h[5] << 16); v.w = h[6] | ((uint32_t)h[7] << 16);
+    reinterpret_cast<uint4*>(recs + (size_t)slot * rec_bytes)[c] = v;
 }
 
 // top[cell]: leaf word (bit31 | depth<<28 | sigma) or the depth-4 node id.
@@ -239,61 +371,10 @@ __global__ void build_top_kernel(const uint32_t* __restrict__ nodes, uint32_t* _
     }
     top[cell] = node;
 }
+#endif
 
-// wide[table*64 + e]: e = (ex<<4)|(ey<<2)|ez, two octree levels per axis (high bit first level).
-__global__ void build_wide_kernel(const uint32_t* __restrict__ nodes, const int* __restrict__ depth,
-                                  const uint32_t* __restrict__ tid, uint32_t* __restrict__ wide,
-                                  uint32_t* __restrict__ wslot, long long capacity) {
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long n = g >> 6;
-    const int e = (int)(g & 63);
-    if (n >= capacity) return;
-    const int d = depth[n];
-    if (d < 0 || (d & 1)) return;            // unreachable node, or odd depth: folded into its parent's table
-    // leaf entry = kLeafBit | (103 + leaf depth) << 23 | sigma: the exponent field of the cube size (vr_march.cuh)
-    const uint32_t ex = (e >> 4) & 3, ey = (e >> 2) & 3, ez = e & 3;
-    const uint32_t oct1 = ((ex >> 1) << 2) | ((ey >> 1) << 1) | (ez >> 1);
-    const size_t o = (size_t)tid[n] * 64 + e;
-    const uint32_t s1 = (uint32_t)n * 8u + oct1;
-    const uint32_t w1 = nodes[s1];
-    if (w1 & kLeafBit) {
-        wide[o] = kLeafBit | ((uint32_t)(103 + d + 1) << 23) | (w1 & 0xffffu);
-        wslot[o] = s1;
-        return;
-    }
-    const uint32_t oct2 = ((ex & 1) << 2) | ((ey & 1) << 1) | (ez & 1);
-    const uint32_t s2 = w1 * 8u + oct2;
-    const uint32_t w2 = nodes[s2];
-    if (w2 & kLeafBit) {
-        wide[o] = kLeafBit | ((uint32_t)(103 + d + 2) << 23) | (w2 & 0xffffu);
-        wslot[o] = s2;
-    } else {
-        wide[o] = tid[w2];
-        wslot[o] = 0;
-    }
-}
-
-// wrecs[entry] = recs[wslot[entry]] for leaf entries (16-byte chunks; 8-byte records as one chunk)
-__global__ void build_wrecs_kernel(const uint32_t* __restrict__ wide, const uint32_t* __restrict__ wslot,
-                                   const unsigned char* __restrict__ recs, unsigned char* __restrict__ wrecs,
-                                   long long n_entries, int rec_bytes) {
-    const int chunks = rec_bytes >= 16 ? rec_bytes / 16 : 1;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long e = gid / chunks;
-    const int c = (int)(gid % chunks);
-    if (e >= n_entries) return;
-    const bool leaf = (wide[e] & kLeafBit) != 0;
-    if (rec_bytes == 8) {
-        reinterpret_cast<uint2*>(wrecs)[e] = leaf ? reinterpret_cast<const uint2*>(recs)[wslot[e]] : make_uint2(0u, 0u);
-        return;
-    }
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (leaf) v = reinterpret_cast<const uint4*>(recs + (size_t)wslot[e] * rec_bytes)[c];
-    reinterpret_cast<uint4*>(wrecs + (size_t)e * rec_bytes)[c] = v;
-}
-
+// retrieve_cursor_lumisphere_kernel (volrend.cu:175-191): descends the wide tables.
 __global__ void probe_kernel(TreeDev tree, float x, float y, float z, int n_out, float* __restrict__ out) {
-    // retrieve_cursor_lumisphere_kernel (volrend.cu:175-191)
     float p[3] = {tree.offset[0] + tree.scale[0] * x, tree.offset[1] + tree.scale[1] * y,
                   tree.offset[2] + tree.scale[2] * z};
     uint32_t u[3];
@@ -301,16 +382,15 @@ __global__ void probe_kernel(TreeDev tree, float x, float y, float z, int n_out,
         p[i] = fmaxf(fminf(p[i], 1.f - 1e-6f), 0.f);
         u[i] = __float2uint_rz(p[i] * 16777216.f);
     }
-    uint32_t node = 0, idx = 0;
-    for (int l = 0;; ++l) {
-        const int sh = 23 - l;
-        const uint32_t oct = (((u[0] >> sh) & 1u) << 2) | (((u[1] >> sh) & 1u) << 1) | ((u[2] >> sh) & 1u);
-        idx = node * 8u + oct;
-        const uint32_t w = tree.nodes[idx];
+    uint32_t T = 0, eidx = 0;
+    for (int j = 0; j < 16; ++j) {
+        const int sh = 22 + tree.wide_p - 2 * j;
+        eidx = T * 64u + ((((u[0] >> sh) & 3u) << 4) | (((u[1] >> sh) & 3u) << 2) | ((u[2] >> sh) & 3u));
+        const uint32_t w = tree.wide[eidx];
         if (w & kLeafBit) break;
-        node = w;
+        T = w;
     }
-    const unsigned short* rec = reinterpret_cast<const unsigned short*>(tree.recs + (size_t)idx * tree.rec_bytes);
+    const unsigned short* rec = reinterpret_cast<const unsigned short*>(tree.wrecs + (size_t)eidx * tree.rec_bytes);
     for (int i = threadIdx.x; i < n_out; i += blockDim.x) out[i] = __half2float(__ushort_as_half(rec[i]));
 }
 
@@ -320,15 +400,38 @@ __global__ void probe_kernel(TreeDev tree, float x, float y, float z, int n_out,
 extern "C" {
 
 const char* vr_last_error(void) { return g_err.c_str(); }
-const char* vr_version(void) { return "volrend_b200 0.1 (sm_100a)"; }
+const char* vr_version(void) { return "volrend_b200 0.2 (sm_100a)"; }
+static bool variant_ok(int kbd, int variant) {
+    switch (kbd) {
+        case -1: return variant_supported<-1>(variant);
+        case 1: return variant_supported<1>(variant);
+        case 4: return variant_supported<4>(variant);
+        case 9: return variant_supported<9>(variant);
+        case 16: return variant_supported<16>(variant);
+        case 25: return variant_supported<25>(variant);
+        default: return false;
+    }
+}
+int vr_variant_supported(int kernel_basis, int variant) { return variant >= 0 && variant_ok(kernel_basis, variant) ? 1 : 0; }
 int vr_set_variant(int variant) {
-    if (variant < 0 || (variant & 15) > 6 || variant > 65535) return fail(VR_EINVAL, "variant must be kind 0..6 (+16*tune)");
+    // accepted when at least one basis size has it; a tree whose basis size lacks it fails at launch
+    bool any = false;
+    for (int kbd : {-1, 1, 4, 9, 16, 25}) any = any || (variant >= 0 && variant_ok(kbd, variant));
+    if (!any) return fail(VR_EINVAL, "kernel variant %d is not built into this library", variant);
     g_variant.store(variant);
     return VR_OK;
 }
-int vr_get_variant(void) {
+int vr_get_variant(void) { return g_variant.load(); }
+int vr_set_max_ctas(int max_ctas) {
+    if (max_ctas < 0) return fail(VR_EINVAL, "max_ctas < 0");
+    g_max_ctas.store(max_ctas);
+    return VR_OK;
+}
+int vr_tree_variant(const vr_tree* t) {
+    if (!t) return -1;
     const int v = g_variant.load();
-    return v == 0 ? kDefaultVariant : v;
+    if (v != 0) return variant_ok(t->dev.kbd, v) ? v : -1;
+    return t->dev.kbd >= 4 ? kVariantQueue : kVariantInline;
 }
 unsigned long long vr_launch_count(void) { return g_launches.load(); }
 
@@ -346,9 +449,9 @@ void vr_tree_destroy(vr_tree* t) {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(t->device);
-    cudaFree(t->nodes); cudaFree(t->recs); cudaFree(t->top); cudaFree(t->extra); cudaFree(t->queues);
+    cudaFree(t->nodes); cudaFree(t->recs); cudaFree(t->top); cudaFree(t->extra);
     cudaFree(t->wide); cudaFree(t->wslot); cudaFree(t->wrecs);
-    cudaFree(t->cam_ring);
+    for (auto& kv : t->res) { cudaFree(kv.second.queues); cudaFree(kv.second.cam_ring); }
     for (int i = 0; i < vr_tree::HostPath::kRing; ++i) {
         cudaFree(t->host.buf[i]);
         if (t->host.rendered[i]) cudaEventDestroy(t->host.rendered[i]);
@@ -396,104 +499,144 @@ static int tree_create_impl(const vr_tree_desc* d, const vr_tree_quant_desc* q, 
     t->data_dim = d->data_dim;
     const long long n_slots = d->capacity * 8;
     const int rec_bytes = rec_bytes_for(kbd);
+    const int TB = 256;
+    Uploader& up = Uploader::get();
+
+    // device scratch, freed on every exit path
+    std::vector<void*> scratch;
+    struct Scratch { std::vector<void*>& v; ~Scratch() { for (void* p : v) cudaFree(p); } } scratch_guard{scratch};
+    auto dalloc = [&](void** p, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+        if (e == cudaSuccess) scratch.push_back(*p);
+        return e;
+    };
+    auto release = [&](void* p) {
+        for (auto& s : scratch) if (s == p) { cudaFree(p); s = nullptr; }
+    };
 
     int32_t* raw_child = nullptr;
-    unsigned short* raw_data = nullptr;
-    int* flags = nullptr;
+    int* flags = nullptr;   // {bad link, changed, node reached twice}
     int* depth = nullptr;
-    struct Tmp { int32_t*& a; unsigned short*& b; int*& c; int*& d; ~Tmp() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); } } tmp{raw_child, raw_data, flags, depth};
-    const size_t child_bytes = (size_t)n_slots * 4, data_bytes = q ? 0 : (size_t)n_slots * d->data_dim * 2;
-    VR_CUDA(cudaMalloc(&raw_child, child_bytes));
-    if (!q) VR_CUDA(cudaMalloc(&raw_data, data_bytes));
-    VR_CUDA(cudaMalloc(&flags, 2 * sizeof(int)));
-    VR_CUDA(cudaMalloc(&depth, (size_t)d->capacity * sizeof(int)));
+    LeafSrc S{};
+    S.n_slots = n_slots; S.data_dim = d->data_dim; S.basis_dim = d->basis_dim; S.kbd = kbd;
+    S.n_total = d->basis_dim; S.n_retain = q ? q->n_retain : 0;
+    VR_CUDA(dalloc((void**)&raw_child, (size_t)n_slots * 4));
+    VR_CUDA(dalloc((void**)&flags, 4 * sizeof(int)));
+    VR_CUDA(dalloc((void**)&depth, (size_t)d->capacity * sizeof(int)));
     VR_CUDA(cudaMalloc(&t->nodes, (size_t)n_slots * 4));
-    VR_CUDA(cudaMalloc(&t->recs, (size_t)n_slots * rec_bytes));
-    VR_CUDA(cudaMalloc(&t->top, kTopCells * 4));
-    VR_CUDA(cudaMalloc(&t->queues, kQueueSlots * 2 * sizeof(unsigned int)));
-    VR_CUDA(cudaMemset(t->queues, 0, kQueueSlots * 2 * sizeof(unsigned int)));
-    VR_CUDA(cudaMalloc(&t->cam_ring, kCamRing * sizeof(CamDev)));
-    VR_CUDA(cudaMemcpy(raw_child, d->child, child_bytes, cudaMemcpyHostToDevice));
-    if (!q) VR_CUDA(cudaMemcpy(raw_data, d->data, data_bytes, cudaMemcpyHostToDevice));
-    VR_CUDA(cudaMemset(flags, 0, 2 * sizeof(int)));
+    VR_CUDA(up.copy(raw_child, d->child, (size_t)n_slots * 4));
+    if (!q) {
+        unsigned short* raw = nullptr;
+        const size_t data_bytes = (size_t)n_slots * d->data_dim * 2;
+        VR_CUDA(dalloc((void**)&raw, data_bytes));
+        VR_CUDA(up.copy(raw, d->data, data_bytes));
+        S.data = raw;
+    } else {
+        const size_t cb = (size_t)q->n_quant * 65536 * 3 * 2, mb = (size_t)q->n_quant * n_slots * 2,
+                     sb = (size_t)n_slots * 2, rb = (size_t)q->n_retain * n_slots * 3 * 2;
+        unsigned short *qc = nullptr, *qm = nullptr, *qs = nullptr, *qr = nullptr;
+        VR_CUDA(dalloc((void**)&qc, cb));
+        VR_CUDA(dalloc((void**)&qm, mb));
+        VR_CUDA(dalloc((void**)&qs, sb));
+        VR_CUDA(up.copy(qc, q->quant_colors, cb));
+        VR_CUDA(up.copy(qm, q->quant_map, mb));
+        VR_CUDA(up.copy(qs, q->sigma, sb));
+        if (q->n_retain > 0) {
+            VR_CUDA(dalloc((void**)&qr, rb));
+            VR_CUDA(up.copy(qr, q->data_retained, rb));
+        }
+        S.colors = qc; S.qmap = qm; S.sigma = qs; S.retained = qr;
+    }
+    VR_CUDA(cudaMemset(flags, 0, 4 * sizeof(int)));
     if (d->extra && (d->format == VR_FMT_SG || d->format == VR_FMT_ASG)) {
         const size_t nf = (size_t)d->basis_dim * (d->format == VR_FMT_SG ? 4 : 11);
         VR_CUDA(cudaMalloc(&t->extra, nf * sizeof(float)));
         VR_CUDA(cudaMemcpy(t->extra, d->extra, nf * sizeof(float), cudaMemcpyHostToDevice));
     }
-    const int TB = 256;
-    const long long rec_work = n_slots * (rec_bytes >= 16 ? rec_bytes / 16 : 1);
-    unsigned short *q_colors = nullptr, *q_map = nullptr, *q_sigma = nullptr, *q_ret = nullptr;
-    struct QTmp { unsigned short *&a, *&b, *&c, *&d; ~QTmp() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); } } qtmp{q_colors, q_map, q_sigma, q_ret};
-    if (!q) {
-        relayout_nodes_kernel<<<(unsigned)((n_slots + TB - 1) / TB), TB>>>(raw_child, raw_data, t->nodes, n_slots,
-                                                                           d->capacity, d->data_dim, flags);
-        relayout_recs_kernel<<<(unsigned)((rec_work + TB - 1) / TB), TB>>>(raw_data, t->recs, n_slots, d->data_dim,
-                                                                           d->basis_dim, kbd, rec_bytes);
-    } else {
-        const size_t cb = (size_t)q->n_quant * 65536 * 3 * 2, mb = (size_t)q->n_quant * n_slots * 2,
-                     sb = (size_t)n_slots * 2, rb = (size_t)q->n_retain * n_slots * 3 * 2;
-        VR_CUDA(cudaMalloc(&q_colors, cb));
-        VR_CUDA(cudaMalloc(&q_map, mb));
-        VR_CUDA(cudaMalloc(&q_sigma, sb));
-        VR_CUDA(cudaMemcpy(q_colors, q->quant_colors, cb, cudaMemcpyHostToDevice));
-        VR_CUDA(cudaMemcpy(q_map, q->quant_map, mb, cudaMemcpyHostToDevice));
-        VR_CUDA(cudaMemcpy(q_sigma, q->sigma, sb, cudaMemcpyHostToDevice));
-        if (q->n_retain > 0) {
-            VR_CUDA(cudaMalloc(&q_ret, rb));
-            VR_CUDA(cudaMemcpy(q_ret, q->data_retained, rb, cudaMemcpyHostToDevice));
-        }
-        quant_nodes_kernel<<<(unsigned)((n_slots + TB - 1) / TB), TB>>>(raw_child, q_sigma, t->nodes, n_slots,
-                                                                        d->capacity, flags);
-        quant_recs_kernel<<<(unsigned)((rec_work + TB - 1) / TB), TB>>>(q_colors, q_map, q_ret, t->recs, n_slots,
-                                                                        d->basis_dim, q->n_retain, kbd, rec_bytes);
-    }
+    relayout_nodes_kernel<<<(unsigned)((n_slots + TB - 1) / TB), TB>>>(raw_child, S, t->nodes, d->capacity, flags);
     VR_CUDA(cudaGetLastError());
-    int h_flags[2] = {0, 0};
-    VR_CUDA(cudaMemcpy(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost));
-    if (h_flags[0]) return fail(VR_EINVAL, "child array has links outside [1, capacity)");
-    // node depths -> max leaf depth
+    release(raw_child);
+
+    // node depths (level-synchronous sweep) -> max leaf depth; validates that the links form a tree
     VR_CUDA(cudaMemset(depth, 0xff, (size_t)d->capacity * sizeof(int)));
     VR_CUDA(cudaMemset(depth, 0, sizeof(int)));
     int max_node_depth = 0;
+    int h_flags[3] = {0, 0, 0};
     for (int level = 0;; ++level) {
-        if (level >= kMaxTreeDepth) return fail(VR_EUNSUPPORTED, "tree deeper than %d levels", kMaxTreeDepth);
-        VR_CUDA(cudaMemset(flags + 1, 0, sizeof(int)));
-        node_depth_kernel<<<(unsigned)((d->capacity + TB - 1) / TB), TB>>>(t->nodes, depth, d->capacity, level, flags + 1);
-        int changed = 0;
-        VR_CUDA(cudaMemcpy(&changed, flags + 1, sizeof(int), cudaMemcpyDeviceToHost));
-        if (!changed) break;
+        if (level >= kMaxTreeDepth) return fail(VR_EUNSUPPORTED, "tree deeper than %d levels (or its child links form a cycle)", kMaxTreeDepth);
+        VR_CUDA(cudaMemsetAsync(flags + 1, 0, sizeof(int)));
+        node_depth_kernel<<<(unsigned)((d->capacity + TB - 1) / TB), TB>>>(t->nodes, depth, d->capacity, level, flags);
+        VR_CUDA(cudaMemcpy(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost));
+        if (h_flags[0]) return fail(VR_EINVAL, "child array has links outside [1, capacity)");
+        if (h_flags[2]) return fail(VR_EINVAL, "child array is not a tree: a node is reachable along two paths");
+        if (!h_flags[1]) break;
         max_node_depth = level + 1;
     }
-    build_top_kernel<<<(kTopCells + TB - 1) / TB, TB>>>(t->nodes, t->top);
-    VR_CUDA(cudaGetLastError());
-    {   // two-levels-per-step tables: ids = running count of even-depth internal nodes, in node order
-        std::vector<int> h_depth((size_t)d->capacity);
-        VR_CUDA(cudaMemcpy(h_depth.data(), depth, (size_t)d->capacity * sizeof(int), cudaMemcpyDeviceToHost));
-        std::vector<uint32_t> h_tid((size_t)d->capacity, 0u);
-        uint32_t n_tab = 0;
-        for (long long n = 0; n < d->capacity; ++n)
-            if (h_depth[(size_t)n] >= 0 && !(h_depth[(size_t)n] & 1)) h_tid[(size_t)n] = n_tab++;
-        if (n_tab >= (1u << 30)) return fail(VR_EUNSUPPORTED, "too many nodes for the wide tables");
-        uint32_t* d_tid = nullptr;
-        struct T2 { uint32_t*& p; ~T2() { cudaFree(p); } } t2{d_tid};
-        VR_CUDA(cudaMalloc(&d_tid, (size_t)d->capacity * 4));
-        VR_CUDA(cudaMemcpy(d_tid, h_tid.data(), (size_t)d->capacity * 4, cudaMemcpyHostToDevice));
-        VR_CUDA(cudaMalloc(&t->wide, (size_t)n_tab * 64 * 4));
-        VR_CUDA(cudaMalloc(&t->wslot, (size_t)n_tab * 64 * 4));
+
+    // two-levels-per-step tables.  Parity: tables hang off the internal nodes of even or of odd depth
+    // (+ the root); the parity with fewer tables wins -- with the other one every table at the deepest
+    // internal level would replicate its 8 leaves 8 times (6-7x more colour-record memory on trees whose
+    // deepest leaves sit at an odd depth).
+    unsigned long long* pcnt = nullptr;
+    VR_CUDA(dalloc((void**)&pcnt, 2 * sizeof(unsigned long long)));
+    VR_CUDA(cudaMemset(pcnt, 0, 2 * sizeof(unsigned long long)));
+    count_parity_kernel<<<(unsigned)((d->capacity + TB - 1) / TB), TB>>>(depth, d->capacity, pcnt);
+    unsigned long long h_pcnt[2] = {0, 0};
+    VR_CUDA(cudaMemcpy(h_pcnt, pcnt, sizeof(h_pcnt), cudaMemcpyDeviceToHost));
+    int wp = (h_pcnt[1] + 1 < h_pcnt[0]) ? 1 : 0;
+    if (const char* e = getenv("VR_WIDE_PARITY")) { if (e[0] == '0') wp = 0; else if (e[0] == '1') wp = 1; }
+    const unsigned long long n_tab64 = wp ? h_pcnt[1] + 1 : h_pcnt[0];
+    if (n_tab64 >= (1ull << 26)) return fail(VR_EUNSUPPORTED, "too many nodes for the wide tables");
+    const uint32_t n_tab = (uint32_t)n_tab64;
+    const long long n_entries = (long long)n_tab * 64;
+    {
+        uint32_t *flag = nullptr, *tid = nullptr;
+        void* tmp = nullptr;
+        size_t tmp_bytes = 0;
+        VR_CUDA(dalloc((void**)&flag, (size_t)d->capacity * 4));
+        VR_CUDA(dalloc((void**)&tid, (size_t)d->capacity * 4));
+        table_flag_kernel<<<(unsigned)((d->capacity + TB - 1) / TB), TB>>>(depth, d->capacity, wp, flag);
+        VR_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flag, tid, (int)d->capacity));
+        VR_CUDA(dalloc(&tmp, tmp_bytes));
+        VR_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, tid, (int)d->capacity));
+        VR_CUDA(cudaMalloc(&t->wide, (size_t)n_entries * 4));
+        VR_CUDA(cudaMalloc(&t->wslot, (size_t)n_entries * 4));
         const long long work = d->capacity * 64;
-        build_wide_kernel<<<(unsigned)((work + TB - 1) / TB), TB>>>(t->nodes, depth, d_tid, t->wide, t->wslot, d->capacity);
+        build_wide_kernel<<<(unsigned)((work + TB - 1) / TB), TB>>>(t->nodes, depth, tid, t->wide, t->wslot, d->capacity, wp);
         VR_CUDA(cudaGetLastError());
-        const long long n_entries = (long long)n_tab * 64;
-        VR_CUDA(cudaMalloc(&t->wrecs, (size_t)n_entries * rec_bytes));
+        release(flag); release(tid); release(tmp);
+    }
+    release(depth);
+    {
+        const size_t wrec_bytes = (size_t)n_entries * rec_bytes;
+        cudaError_t e = cudaMalloc(&t->wrecs, wrec_bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(VR_ENOMEM, "colour records of the wide tables need %.2f GB (%lld entries x %d B): %s", wrec_bytes / 1e9,
+                        n_entries, rec_bytes, cudaGetErrorString(e));
+        }
         const long long rwork = n_entries * (rec_bytes >= 16 ? rec_bytes / 16 : 1);
-        build_wrecs_kernel<<<(unsigned)((rwork + TB - 1) / TB), TB>>>(t->wide, t->wslot, t->recs, t->wrecs, n_entries, rec_bytes);
+        build_wrecs_kernel<<<(unsigned)((rwork + TB - 1) / TB), TB>>>(t->wslot, S, t->wrecs, n_entries, rec_bytes);
         VR_CUDA(cudaGetLastError());
-        VR_CUDA(cudaDeviceSynchronize());
-        t->n_tables = n_tab;
+    }
+#ifdef VR_EXPERIMENTS
+    {   // slot-indexed records and the dense top grid of the experiment kernels
+        VR_CUDA(cudaMalloc(&t->recs, (size_t)n_slots * rec_bytes));
+        VR_CUDA(cudaMalloc(&t->top, kTopCells * 4));
+        const long long rec_work = n_slots * (rec_bytes >= 16 ? rec_bytes / 16 : 1);
+        relayout_recs_kernel<<<(unsigned)((rec_work + TB - 1) / TB), TB>>>(S, t->recs, rec_bytes);
+        build_top_kernel<<<(kTopCells + TB - 1) / TB, TB>>>(t->nodes, t->top);
+        VR_CUDA(cudaGetLastError());
     }
     VR_CUDA(cudaDeviceSynchronize());
-    g_launches += 5;
+#else
+    VR_CUDA(cudaDeviceSynchronize());
+    // the product kernels read the tables and the table-indexed records only
+    cudaFree(t->nodes); t->nodes = nullptr;
+    cudaFree(t->wslot); t->wslot = nullptr;
+#endif
+    t->n_tables = n_tab;
+    g_launches += 7;
 
     TreeDev& D = t->dev;
     D.nodes = t->nodes; D.recs = t->recs; D.top = t->top; D.extra = t->extra;
@@ -502,16 +645,22 @@ static int tree_create_impl(const vr_tree_desc* d, const vr_tree_quant_desc* q, 
     D.ndc_width = d->use_ndc ? d->ndc_width : -1.f;  // data_spec.hpp:47
     D.ndc_height = d->ndc_height; D.ndc_focal = d->ndc_focal;
     D.N = d->N; D.format = d->format; D.basis_dim = d->basis_dim; D.kbd = kbd;
-    D.rec_bytes = rec_bytes; D.max_depth = max_node_depth + 1;
-    t->info.capacity = d->capacity; t->info.max_depth = D.max_depth; t->info.rec_bytes = rec_bytes;
-    t->info.node_bytes = n_slots * 4; t->info.rec_total_bytes = n_slots * (long long)rec_bytes;
-    t->info.top_bytes = kTopCells * 4;
+    D.rec_bytes = rec_bytes; D.max_depth = max_node_depth + 1; D.wide_p = wp;
+    vr_tree_info& I = t->info;
+    I.capacity = d->capacity; I.max_depth = D.max_depth; I.rec_bytes = rec_bytes;
+    I.node_bytes = n_slots * 4; I.rec_total_bytes = n_slots * (long long)rec_bytes;
+    I.top_bytes = kTopCells * 4;
+    I.kernel_basis = kbd; I.wide_parity = wp; I.n_tables = n_tab;
+    I.wide_bytes = n_entries * 4; I.wrecs_bytes = n_entries * (long long)rec_bytes;
+    I.kernel_bytes = I.wide_bytes + I.wrecs_bytes;
+    I.device_bytes = I.kernel_bytes + (t->nodes ? I.node_bytes : 0) + (t->recs ? I.rec_total_bytes : 0) +
+                     (t->wslot ? I.wide_bytes : 0) + (t->top ? I.top_bytes : 0);
     if (const char* e = getenv("VR_L2_PERSIST")) {
         if (atoi(e) > 0) {
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, t->device);
             cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, t->device);
-            size_t want = (size_t)n_slots * 4;
+            size_t want = (size_t)n_entries * 4;
             if (want > (size_t)max_window) want = (size_t)max_window;
             size_t carve = want < (size_t)max_persist ? want : (size_t)max_persist;
             if (carve > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess)
@@ -556,13 +705,41 @@ void fill_cam(CamDev& c, const vr_camera* s) {
     memcpy(c.c2w, s->c2w, sizeof(c.c2w));
 }
 
+// Launch resources of (tree, stream); created on the first launch on that stream.
+int stream_res(vr_tree* t, cudaStream_t stream, StreamRes*& out) {
+    std::lock_guard<std::mutex> lk(t->res_mu);
+    auto it = t->res.find(stream);
+    if (it == t->res.end()) {
+        StreamRes r;
+        VR_CUDA(cudaMalloc(&r.queues, kQueueSlots * 2 * sizeof(unsigned int)));
+        cudaError_t e = cudaMalloc(&r.cam_ring, kCamRing * sizeof(CamDev));
+        if (e == cudaSuccess) e = cudaMemset(r.queues, 0, kQueueSlots * 2 * sizeof(unsigned int));   // legacy stream: ordered before later launches
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            cudaFree(r.queues); cudaFree(r.cam_ring);
+            return fail(VR_ECUDA, "stream resources: %s", cudaGetErrorString(e));
+        }
+        it = t->res.emplace(stream, r).first;
+    }
+    out = &it->second;
+    return VR_OK;
+}
+
 int dispatch(const vr_tree* t, LaunchDev& P, bool count, bool surface, cudaStream_t stream) {
     LaunchCfg cfg;
     cfg.variant = vr_get_variant();
+    if (!variant_ok(t->dev.kbd, cfg.variant))
+        return fail(VR_EUNSUPPORTED, "kernel variant %d is not available for kernel basis %d", cfg.variant, t->dev.kbd);
+    cfg.max_ctas = g_max_ctas.load();
     cfg.count = count; cfg.surface = surface; cfg.num_sms = t->num_sms; cfg.stream = stream;
     vr_tree* mt = const_cast<vr_tree*>(t);
-    cfg.queue = mt->queues + 2 * (mt->next_queue.fetch_add(1) % kQueueSlots);
-    cfg.l2_window = t->nodes;
+    StreamRes* sr = nullptr;
+    if (int rc = stream_res(mt, stream, sr)) return rc;
+    {
+        std::lock_guard<std::mutex> lk(mt->res_mu);
+        cfg.queue = sr->queues + 2 * (sr->next_queue++ % kQueueSlots);
+    }
+    cfg.l2_window = t->wide;
     cfg.l2_window_bytes = t->l2_window_bytes;
     static const bool no_pdl = getenv("VR_NO_PDL") != nullptr && atoi(getenv("VR_NO_PDL")) > 0;
     cfg.pdl = !no_pdl;
@@ -642,17 +819,21 @@ int vr_render_batch(const vr_tree* t, const vr_camera* cams, int n_views, const 
     if (n_views > 1) {
         // cameras go through a device ring owned by the tree (no allocation on the launch path: a
         // stream-ordered pool would hand memory back to the OS at every synchronisation)
+        // (the ring belongs to (tree, stream): a slot is rewritten only by a copy that is stream-ordered
+        // behind the launch that read it)
         vr_tree* mt = const_cast<vr_tree*>(t);
+        StreamRes* sr = nullptr;
+        if ((rc = stream_res(mt, stream, sr))) return rc;
         unsigned int slot;
         {
-            std::lock_guard<std::mutex> lk(mt->cam_mu);
-            if (mt->cam_pos + (unsigned int)n_views > (unsigned int)kCamRing) mt->cam_pos = 0;  // no wrap inside a batch
-            slot = mt->cam_pos;
-            mt->cam_pos += (unsigned int)n_views;
+            std::lock_guard<std::mutex> lk(mt->res_mu);
+            if (sr->cam_pos + (unsigned int)n_views > (unsigned int)kCamRing) sr->cam_pos = 0;  // no wrap inside a batch
+            slot = sr->cam_pos;
+            sr->cam_pos += (unsigned int)n_views;
         }
         std::vector<CamDev> h(n_views);
         for (int i = 0; i < n_views; ++i) fill_cam(h[i], &cams[i]);
-        CamDev* dcams = mt->cam_ring + slot;
+        CamDev* dcams = sr->cam_ring + slot;
         VR_CUDA(cudaMemcpyAsync(dcams, h.data(), sizeof(CamDev) * n_views, cudaMemcpyHostToDevice, stream));
         // pageable source: the copy has been staged when cudaMemcpyAsync returns
         P.cams = dcams;
@@ -805,11 +986,53 @@ int vr_render_frames_host(const vr_tree* t, const vr_camera* cams, int n_views, 
     return VR_OK;
 }
 
+int vr_dev_alloc(size_t bytes, void** ptr) {
+    if (!ptr) return fail(VR_EINVAL, "null argument");
+    *ptr = nullptr;
+    VR_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
+    return VR_OK;
+}
+int vr_dev_free(void* ptr) {
+    VR_CUDA(cudaFree(ptr));
+    return VR_OK;
+}
+int vr_ipc_export(void* dev_ptr, unsigned char handle_out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!dev_ptr || !handle_out) return fail(VR_EINVAL, "null argument");
+    cudaIpcMemHandle_t h;
+    VR_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle_out, &h, 64);
+    return VR_OK;
+}
+int vr_ipc_open(const unsigned char handle[64], void** ptr_out) {
+    if (!handle || !ptr_out) return fail(VR_EINVAL, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    VR_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return VR_OK;
+}
+int vr_ipc_close(void* ptr) {
+    VR_CUDA(cudaIpcCloseMemHandle(ptr));
+    return VR_OK;
+}
+int vr_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
+    if (bytes == 0) return VR_OK;
+    if (!dst || !src) return fail(VR_EINVAL, "null argument");
+    VR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return VR_OK;
+}
+
 int vr_probe_lumisphere(const vr_tree* t, const float xyz[3], float* out_dev, void* stream_) {
     if (!t || !xyz || !out_dev) return fail(VR_EINVAL, "null argument");
-    const int n_out = t->data_dim - 1;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(VR_ENODEVICE, "no CUDA device");
+    if (dev != t->device) return fail(VR_EINVAL, "tree lives on device %d but device %d is current", t->device, dev);
     if (t->dev.kbd > 0 && t->dev.kbd != t->dev.basis_dim)
         return fail(VR_EUNSUPPORTED, "probe unavailable for basis_dim %d (only coefficient 0 is resident)", t->dev.basis_dim);
+    // the resident record holds the colour coefficients only: 3 per RGBA leaf, 3*basis_dim otherwise
+    // (extra trailing channels of an over-wide data_dim are not kept)
+    const int resident = t->dev.kbd < 0 ? 3 : 3 * t->dev.kbd;
+    const int n_out = t->data_dim - 1 < resident ? t->data_dim - 1 : resident;
     probe_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(t->dev, xyz[0], xyz[1], xyz[2], n_out, out_dev);
     VR_CUDA(cudaGetLastError());
     g_launches += 1;

@@ -6,10 +6,14 @@
 
 namespace vrb {
 
-// variant: 1 tile kernel, 2 tile + TMA top grid, 3 persistent, 4 persistent + TMA top grid,
-//          5 persistent + deferred shading, 6 same + TMA top grid
+// variant = kind + 16 * tune; 0 = the default for the tree's basis size.
+//   kind 7: persistent warps + warp-shared shading queue (vr_march_q.cuh), >= 4 basis functions
+//   kind 3, tune 193: persistent warps, inline shading (vr_march.cuh)
+//   -DVR_EXPERIMENTS only: 1 tile kernel, 2 tile + TMA top grid, 3 persistent (+ tuning bits),
+//   4 persistent + TMA top grid, 5 persistent + deferred shading, 6 same + TMA top grid
 struct LaunchCfg {
     int variant;
+    int max_ctas;    // > 0: cap the persistent grid (leaves SMs to a concurrent copy/collective kernel)
     bool count;      // instrumented build: accumulate vr_counters
     bool surface;    // write a cudaSurfaceObject instead of linear memory
     int num_sms;
@@ -23,11 +27,20 @@ struct LaunchCfg {
 template <int KBD>
 cudaError_t launch_march(LaunchDev& P, const LaunchCfg& cfg);
 
+template <int KBD>
+bool variant_supported(int variant);
+
 extern template cudaError_t launch_march<-1>(LaunchDev&, const LaunchCfg&);
 extern template cudaError_t launch_march<1>(LaunchDev&, const LaunchCfg&);
 extern template cudaError_t launch_march<4>(LaunchDev&, const LaunchCfg&);
 extern template cudaError_t launch_march<9>(LaunchDev&, const LaunchCfg&);
 extern template cudaError_t launch_march<16>(LaunchDev&, const LaunchCfg&);
 extern template cudaError_t launch_march<25>(LaunchDev&, const LaunchCfg&);
+extern template bool variant_supported<-1>(int);
+extern template bool variant_supported<1>(int);
+extern template bool variant_supported<4>(int);
+extern template bool variant_supported<9>(int);
+extern template bool variant_supported<16>(int);
+extern template bool variant_supported<25>(int);
 
 }  // namespace vrb

@@ -1,7 +1,18 @@
 // vr_kernels_inst.cu -- instantiates the march kernels for one basis size (-DVR_KBD=...).
 // Compiled six times (RGBA, SH/SG/ASG 1, 4, 9, 16, 25) so the builds run in parallel.
+//
+// Product kernels:
+//   kind 7           march_queue_kernel (vr_march_q.cuh): default for >= 4 basis functions
+//   kind 3, tune 193 march_persistent_kernel with inline shading: default for RGBA / 1 basis
+//                    function (their shading is a handful of instructions), and the A/B partner of
+//                    the queue kernel in the parity tests and the bench
+// Built only with -DVR_EXPERIMENTS (make lib SUFFIX=_exp EXTRA=-DVR_EXPERIMENTS): the measured and
+// rejected structures of round 1 -- CTA-per-tile kernel, TMA-staged top grid, deferred shading,
+// software-pipelined march, tuning knobs.
+#include <mutex>
+
 #include "vr_kernels.h"
-#include "vr_march.cuh"
+#include "vr_march_q.cuh"
 
 #ifndef VR_KBD
 #error "compile with -DVR_KBD=<-1|1|4|9|16|25>"
@@ -11,37 +22,42 @@ namespace vrb {
 
 namespace {
 
+// Resident CTAs of a persistent kernel, cached per (device, kernel, dynamic shared memory).
 template <typename K>
 int resident_ctas(K kernel, size_t smem, int num_sms) {
+    struct Entry { int device; const void* fn; size_t smem; int per_sm; };
+    static std::mutex mu;
+    static Entry cache[32];
+    static int n_cache = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    std::lock_guard<std::mutex> lk(mu);
+    for (int i = 0; i < n_cache; ++i)
+        if (cache[i].device == dev && cache[i].fn == fn && cache[i].smem == smem) return cache[i].per_sm * num_sms;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem) != cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
         per_sm = 1;
+    }
+    if (n_cache < 32) cache[n_cache++] = Entry{dev, fn, smem, per_sm};
     return per_sm * num_sms;
 }
 
-template <int KBD, bool TOP, bool COUNT, int OUT>
-cudaError_t launch_tile(const LaunchDev& P, const LaunchCfg& cfg) {
-    const size_t smem = march_smem_bytes<TOP>(P.tree.max_depth) + basis_smem_bytes<KBD>();
-    dim3 grid((P.w + kTileW - 1) / kTileW, (P.h + kTileH - 1) / kTileH, P.n_views);
-    march_tile_kernel<KBD, TOP, COUNT, OUT><<<grid, kBlock, smem, cfg.stream>>>(P);
-    return cudaGetLastError();
-}
-
-template <int KBD, bool TOP, bool COUNT, int OUT, int TUNE = 0>
-cudaError_t launch_persistent(LaunchDev& P, const LaunchCfg& cfg) {
-    const size_t smem = march_smem_bytes<TOP, (TUNE & kTuneWide) != 0 && !TOP>(P.tree.max_depth) + basis_smem_bytes<KBD>();
-    static int cached_ctas = 0, cached_depth = -1;
-    if (cached_ctas == 0 || cached_depth != P.tree.max_depth) {
-        cached_ctas = resident_ctas(march_persistent_kernel<KBD, TOP, COUNT, OUT, TUNE>, smem, cfg.num_sms);
-        cached_depth = P.tree.max_depth;
-    }
+void set_work(LaunchDev& P, const LaunchCfg& cfg) {
     P.tiles_x = (P.w + kTW - 1) / kTW;
     P.tiles_y = (P.h + kTH - 1) / kTH;
     P.n_tiles = P.tiles_x * P.tiles_y * P.n_views;
     set_div((uint32_t)(P.tiles_x * P.tiles_y), P.div_view_mul, P.div_view_shift);
     set_div((uint32_t)P.tiles_x, P.div_row_mul, P.div_row_shift);
     P.work_counter = cfg.queue;
-    int grid = cached_ctas;
+}
+
+template <typename K>
+cudaError_t launch_persistent_grid(K kernel, size_t smem, LaunchDev& P, const LaunchCfg& cfg) {
+    set_work(P, cfg);
+    int grid = resident_ctas(kernel, smem, cfg.num_sms);
+    if (cfg.max_ctas > 0 && grid > cfg.max_ctas) grid = cfg.max_ctas;
     const int need = (P.n_tiles + (kBlock / 32) - 1) / (kBlock / 32);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
@@ -64,72 +80,112 @@ cudaError_t launch_persistent(LaunchDev& P, const LaunchCfg& cfg) {
         ++na;
     }
     lc.attrs = attr; lc.numAttrs = na;
-    return cudaLaunchKernelEx(&lc, march_persistent_kernel<KBD, TOP, COUNT, OUT, TUNE>, P);
+    return cudaLaunchKernelEx(&lc, kernel, P);
+}
+
+template <int KBD, bool TOP, bool COUNT, int OUT, int TUNE = 0>
+cudaError_t launch_persistent(LaunchDev& P, const LaunchCfg& cfg) {
+    const size_t smem = march_smem_bytes<TOP, (TUNE & kTuneWide) != 0 && !TOP>(P.tree.max_depth) + basis_smem_bytes<KBD>();
+    return launch_persistent_grid(march_persistent_kernel<KBD, TOP, COUNT, OUT, TUNE>, smem, P, cfg);
+}
+
+template <int KBD, bool COUNT, int OUT>
+cudaError_t launch_queue(LaunchDev& P, const LaunchCfg& cfg) {
+    if constexpr (KBD >= 4) {
+        const size_t smem = queue_smem_bytes<KBD>(P.tree.max_depth);
+        return launch_persistent_grid(march_queue_kernel<KBD, COUNT, OUT>, smem, P, cfg);
+    } else {
+        return cudaErrorInvalidValue;
+    }
+}
+
+#ifdef VR_EXPERIMENTS
+template <int KBD, bool TOP, bool COUNT, int OUT>
+cudaError_t launch_tile(const LaunchDev& P, const LaunchCfg& cfg) {
+    const size_t smem = march_smem_bytes<TOP>(P.tree.max_depth) + basis_smem_bytes<KBD>();
+    dim3 grid((P.w + kTileW - 1) / kTileW, (P.h + kTileH - 1) / kTileH, P.n_views);
+    march_tile_kernel<KBD, TOP, COUNT, OUT><<<grid, kBlock, smem, cfg.stream>>>(P);
+    return cudaGetLastError();
 }
 
 template <int KBD, bool TOP, bool COUNT, int OUT>
 cudaError_t launch_deferred(LaunchDev& P, const LaunchCfg& cfg) {
     const size_t smem = deferred_smem_bytes<TOP>(P.tree.max_depth);
-    static int cached_ctas = 0, cached_depth = -1;
-    if (cached_ctas == 0 || cached_depth != P.tree.max_depth) {
-        cached_ctas = resident_ctas(march_deferred_kernel<KBD, TOP, COUNT, OUT>, smem, cfg.num_sms);
-        cached_depth = P.tree.max_depth;
-    }
-    P.tiles_x = (P.w + kTW - 1) / kTW;
-    P.tiles_y = (P.h + kTH - 1) / kTH;
-    P.n_tiles = P.tiles_x * P.tiles_y * P.n_views;
-    set_div((uint32_t)(P.tiles_x * P.tiles_y), P.div_view_mul, P.div_view_shift);
-    set_div((uint32_t)P.tiles_x, P.div_row_mul, P.div_row_shift);
-    P.work_counter = cfg.queue;
-    int grid = cached_ctas;
+    set_work(P, cfg);
+    int grid = resident_ctas(march_deferred_kernel<KBD, TOP, COUNT, OUT>, smem, cfg.num_sms);
     const int need = (P.n_tiles + (kBlock / 32) - 1) / (kBlock / 32);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     march_deferred_kernel<KBD, TOP, COUNT, OUT><<<grid, kBlock, smem, cfg.stream>>>(P);
     return cudaGetLastError();
 }
+#endif
+
+constexpr int kInline = 193;  // cache hints + wide tables + table-indexed records
 
 }  // namespace
 
+// variant 0: the default for this basis size.  kind = variant & 15, tune = variant >> 4.
+template <int KBD>
+bool variant_supported(int variant) {
+    if (variant == 0) return true;
+    const int kind = variant & 15, tune = variant >> 4;
+    if (kind == 7) return tune == 0 && KBD >= 4;
+    if (kind == 3 && tune == kInline) return true;
+#ifdef VR_EXPERIMENTS
+    if (kind == 3) return tune == 0 || tune == 1 || tune == 2 || tune == 3 || tune == 8 || tune == 10 || tune == 16 ||
+                          tune == 17 || tune == 64 || tune == 65;
+    if (kind >= 1 && kind <= 6) return tune == 0;
+#endif
+    return false;
+}
+
 template <int KBD>
 cudaError_t launch_march(LaunchDev& P, const LaunchCfg& cfg) {
-    const int kind = cfg.variant & 15, tune = cfg.variant >> 4;
-    const bool top = (kind == 2 || kind == 4 || kind == 6);
-    const bool persistent = (kind == 3 || kind == 4);
-    const bool deferred = kind >= 5;
-    if (kind == 3 && tune && !cfg.surface && !cfg.count) {  // measurement knobs on the persistent kernel
+    int variant = cfg.variant;
+    if (!variant_supported<KBD>(variant)) return cudaErrorInvalidValue;
+    if (variant == 0) variant = KBD >= 4 ? 7 : 3 + 16 * kInline;
+    const int kind = variant & 15, tune = variant >> 4;
+    const bool queue = kind == 7;
+    if (cfg.surface) {  // drop-in launch_renderer path writing the caller's cudaArray
+        return queue ? launch_queue<KBD, false, kOutSurface>(P, cfg)
+                     : launch_persistent<KBD, false, false, kOutSurface, kInline>(P, cfg);
+    }
+    if (cfg.count) {  // instrumented builds
+        return queue ? launch_queue<KBD, true, kOutLinear>(P, cfg)
+                     : launch_persistent<KBD, false, true, kOutLinear, kInline>(P, cfg);
+    }
+    if (queue) return launch_queue<KBD, false, kOutLinear>(P, cfg);
+    if (kind == 3 && tune == kInline) return launch_persistent<KBD, false, false, kOutLinear, kInline>(P, cfg);
+#ifdef VR_EXPERIMENTS
+    if (kind == 3) {
         switch (tune) {
+            case 0: return launch_persistent<KBD, false, false, kOutLinear>(P, cfg);
             case 1: return launch_persistent<KBD, false, false, kOutLinear, 1>(P, cfg);
             case 2: return launch_persistent<KBD, false, false, kOutLinear, 2>(P, cfg);
             case 3: return launch_persistent<KBD, false, false, kOutLinear, 3>(P, cfg);
             case 8: return launch_persistent<KBD, false, false, kOutLinear, 8>(P, cfg);
             case 10: return launch_persistent<KBD, false, false, kOutLinear, 10>(P, cfg);
-            case 17: return launch_persistent<KBD, false, false, kOutLinear, 17>(P, cfg);
-            case 65: return launch_persistent<KBD, false, false, kOutLinear, 65>(P, cfg);
-            case 193: return launch_persistent<KBD, false, false, kOutLinear, 193>(P, cfg);
-            case 64: return launch_persistent<KBD, false, false, kOutLinear, 64>(P, cfg);
             case 16: return launch_persistent<KBD, false, false, kOutLinear, 16>(P, cfg);
+            case 17: return launch_persistent<KBD, false, false, kOutLinear, 17>(P, cfg);
+            case 64: return launch_persistent<KBD, false, false, kOutLinear, 64>(P, cfg);
+            case 65: return launch_persistent<KBD, false, false, kOutLinear, 65>(P, cfg);
             default: return cudaErrorInvalidValue;
         }
     }
-    if (cfg.surface) {  // drop-in launch_renderer path: default kernel writing the caller's cudaArray
-        return launch_persistent<KBD, false, false, kOutSurface, 193>(P, cfg);
+    switch (kind) {
+        case 1: return launch_tile<KBD, false, false, kOutLinear>(P, cfg);
+        case 2: return launch_tile<KBD, true, false, kOutLinear>(P, cfg);
+        case 4: return launch_persistent<KBD, true, false, kOutLinear>(P, cfg);
+        case 5: return launch_deferred<KBD, false, false, kOutLinear>(P, cfg);
+        case 6: return launch_deferred<KBD, true, false, kOutLinear>(P, cfg);
+        default: break;
     }
-    if (cfg.count) {  // instrumented build of the default kernel
-        return launch_persistent<KBD, false, true, kOutLinear, 193>(P, cfg);
-    }
-    if (deferred) {
-        return top ? launch_deferred<KBD, true, false, kOutLinear>(P, cfg)
-                   : launch_deferred<KBD, false, false, kOutLinear>(P, cfg);
-    }
-    if (persistent) {
-        return top ? launch_persistent<KBD, true, false, kOutLinear>(P, cfg)
-                   : launch_persistent<KBD, false, false, kOutLinear>(P, cfg);
-    }
-    return top ? launch_tile<KBD, true, false, kOutLinear>(P, cfg)
-               : launch_tile<KBD, false, false, kOutLinear>(P, cfg);
+#endif
+    return cudaErrorInvalidValue;
 }
 
 template cudaError_t launch_march<VR_KBD>(LaunchDev&, const LaunchCfg&);
+template bool variant_supported<VR_KBD>(int);
 
 }  // namespace vrb

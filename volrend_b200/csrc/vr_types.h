@@ -27,8 +27,8 @@ struct TreeDev {
     const uint32_t* nodes;
     const unsigned char* recs;
     const uint32_t* top;
-    // two-levels-per-step view of the same octree (variant "wide"): one 64-entry table per internal
-    // node of even depth; entry = table id of the grandchild, or leaf word:
+    // two-levels-per-step view of the same octree: one 64-entry table per internal node whose depth has
+    // parity wide_p (plus the root); entry = table id of the grandchild, or leaf word:
     //   kLeafBit | (103 + leaf depth) << 23 | sigma   (bits 23..30 = fp32 exponent of the cube size)
     const uint32_t* wide;
     const uint32_t* wslot;   // parallel array: the leaf's slot (node*8+oct) for record lookup
@@ -43,6 +43,7 @@ struct TreeDev {
     int32_t kbd;        // kernel basis: -1 RGBA, 1, 4, 9, 16, 25 (others collapse to 1)
     int32_t rec_bytes;
     int32_t max_depth;
+    int32_t wide_p;     // parity of the depths whose internal nodes own a wide table (0 or 1)
 };
 
 struct CamDev {
