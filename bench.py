@@ -260,10 +260,12 @@ def cli_leg(scene: Scene, exe: str, n_frames: int = N_POSES):
         best = None
         for _ in range(2):   # first run pays the page cache / module load
             r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-            m = re.search(r"([0-9.]+) ms per frame", r.stdout)
+            # the loader's "INFO: Scale %f %f %f" has no newline (src/n3tree.cpp:264), so the "ms per frame" line is
+            # glued to it; the "fps" line (main_headless.cpp:231) stands alone: ms = 1000 / fps
+            m = re.search(r"^\s*([0-9]+\.[0-9]+) fps\s*$", r.stdout, re.M)
             if r.returncode != 0 or not m:
                 return {"error": (r.stderr or r.stdout)[-300:]}
-            ms = float(m.group(1))
+            ms = 1000.0 / float(m.group(1))
             best = ms if best is None else min(best, ms)
         return {"ms_per_frame": best, "value": W * H / best / 1e3, "unit": "Mrays/s", "frames": n_frames,
                 "binary": os.path.relpath(exe, ROOT),
@@ -277,7 +279,7 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     with StdoutToStderr():
-        line = _reference_line(args)
+        line = reference_config4(args) if args.workload == "config4" else _reference_line(args)
     print(json.dumps(line), flush=True)
 
 
@@ -351,16 +353,22 @@ class PeerGather:
         obj = [bytes(handle.raw) if rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
         if rank == 0:
-            self.dst = self.base.value
+            self.root = self.base.value           # start of rank 0's buffer as THIS process addresses it
         else:
             p = ctypes.c_void_p()
             assert lib.vr_ipc_open(obj[0], ctypes.byref(p)) == 0, lib.vr_last_error()
             self.mapped = p
-            self.dst = p.value + rank * bytes_per_rank
+            self.root = p.value
+        self.dst = self.root + rank * bytes_per_rank
 
     def send(self, src_ptr: int, offset: int, nbytes: int, stream_ptr: int):
         assert self.lib.vr_copy_async(ctypes.c_void_p(self.dst + offset), ctypes.c_void_p(src_ptr), nbytes,
                                       ctypes.c_void_p(stream_ptr)) == 0, self.lib.vr_last_error()
+
+    def send2d(self, root_offset: int, dpitch: int, src_ptr: int, spitch: int, width: int, rows: int, stream_ptr: int):
+        """Strided (band) copy to byte `root_offset` of rank 0's buffer."""
+        assert self.lib.vr_copy2d_async(ctypes.c_void_p(self.root + root_offset), dpitch, ctypes.c_void_p(src_ptr), spitch,
+                                        width, rows, ctypes.c_void_p(stream_ptr)) == 0, self.lib.vr_last_error()
 
     def close(self):
         if self.mapped is not None:
@@ -369,8 +377,221 @@ class PeerGather:
             self.lib.vr_dev_free(self.base)
 
 
+C4_W, C4_H, C4_FX, C4_POSES, C4_BAND = 1920, 1080, 1500.0, 40, 8
+C4_WORKLOAD = ("BASELINE config 4: synthetic depth-11 SH25 octree (gyroid shell, seed 0), 1920x1080, 40 orbit poses per step, "
+               "every frame ray-tile sharded over the GPUs (interleaved 8-row bands)")
+
+
+def config4_scene():
+    from volrend_b200 import synth
+    st = synth.make_tree("gyroid_small", depth=11, basis_dim=25, seed=0, band_cells=1.0)
+    poses = synth.nerf_synthetic_test_poses(C4_POSES, radius=1.6, elev_deg=25.0)
+    return st, poses
+
+
+def reference_config4(args):
+    """--impl reference --workload config4: the reference kernel on the same tree and poses at 1080p."""
+    from volrend_b200 import synth
+    from oracle import ref_binding as rb
+    import torch
+    line = {"impl": "reference", "metric": "Mrays/s @ 1920x1080", "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": C4_WORKLOAD}}
+    if not (rb.available() and torch.cuda.is_available()):
+        line["unavailable"] = "oracle/_ref not built or no GPU"
+        return line
+    st, poses = config4_scene()
+    path = "/tmp/vr_config4_tree.npz"
+    if not os.path.exists(path):
+        st.save_npz(path)
+    rt = rb.RefTree(path)
+    c12 = np.stack([synth.c2w_to_colmajor12(p) for p in poses])
+    opt = rb.make_options()
+    for _ in range(args.warmup):
+        rt.time_frames(C4_W, C4_H, C4_FX, C4_FX, c12, opt)
+    ms = [rt.time_frames(C4_W, C4_H, C4_FX, C4_FX, c12, opt) for _ in range(args.steps)]
+    host = torch.empty((C4_POSES, C4_H, C4_W, 4), dtype=torch.uint8).pin_memory()
+    ms_e = [rt.time_frames(C4_W, C4_H, C4_FX, C4_FX, c12, opt, with_d2h=True, host_out=host) for _ in range(args.steps)]
+    rt.close()
+    t, te = float(np.mean(ms)), float(np.mean(ms_e))
+    rays = C4_W * C4_H * C4_POSES
+    line.update({"value": rays / t / 1e3, "ms_per_step": t, "gpu_launches": C4_POSES * args.steps,
+                 "reference": "volrend::launch_renderer (oracle/_ref, -arch=sm_100), one GPU: the reference has no multi-GPU path",
+                 "e2e": {"value": rays / te / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": 48 * C4_POSES,
+                         "d2h_bytes_per_step": 4 * C4_W * C4_H * C4_POSES}})
+    return line
+
+
+def main_config4(args, rank, world, local_rank):
+    """--workload config4: STRONG scaling of one fixed job (40 frames of 1920x1080 on the depth-11 SH25 tree).
+    Every rank renders its bands of ALL frames with one launch (vr_render_bands_batch); the copy engines scatter
+    the compact bands straight into the frames on rank 0 (2-D peer copies into an IPC-mapped buffer)."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from volrend_b200 import Camera, N3Tree, RenderOptions, lib, render_bands_batch, render_batch
+    from volrend_b200 import dist as vd
+    st, poses = config4_scene()
+    tree = N3Tree.from_synth(st)
+    info = tree.info()
+    cams = []
+    for p in poses:
+        c = Camera(C4_W, C4_H, C4_FX, C4_FX)
+        c.set_c2w(p)
+        cams.append(c)
+    opt = RenderOptions()
+    row, frame = 4 * C4_W, 4 * C4_W * C4_H
+    rows = vd.band_rows(C4_H, C4_BAND, world, rank)
+    plan = vd.band_scatter_plan(C4_W, C4_H, C4_BAND, world, rank)
+    peer = PeerGather(dist, lib(), rank, world, frame * C4_POSES // world + 1) if world > 1 else None
+    if world == 1:
+        frames = torch.zeros((C4_POSES, C4_H, C4_W, 4), dtype=torch.uint8, device=dev)
+    local = [torch.zeros((C4_POSES, max(rows, 1), C4_W, 4), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    sent = [None, None]
+
+    # work counters of the whole job (rank 0, untimed) for the roofline
+    S = D = SH = HIT = FETCH = 0
+    if rank == 0:
+        cnt = torch.zeros(5, dtype=torch.int64, device=dev)
+        tmp = torch.zeros((C4_POSES, C4_H, C4_W, 4), dtype=torch.uint8, device=dev) if world > 1 else frames
+        render_batch(tree, cams, opt, tmp, counters=cnt)
+        torch.cuda.synchronize()
+        S, D, SH, HIT, FETCH = [int(v) for v in cnt.cpu().tolist()]
+        solo = tmp[::13].cpu().numpy()           # single-GPU frames 0, 13, 26, 39 for the reassembly check
+        del tmp
+    a_step = 4 * D + 2 * S + 6 * 25 * SH + 4 * C4_W * C4_H * C4_POSES
+    c_step = 4 * FETCH + info["rec_bytes"] * SH + 4 * C4_W * C4_H * C4_POSES
+
+    def step(i):
+        cur = torch.cuda.current_stream()
+        if world == 1:
+            render_batch(tree, cams, opt, frames)
+            return
+        k = i & 1
+        if sent[k] is not None:
+            cur.wait_event(sent[k])
+        render_bands_batch(tree, cams, opt, C4_BAND, world, rank, local[k])
+        done = torch.cuda.Event()
+        done.record(cur)
+        comm.wait_event(done)
+        base = local[k].data_ptr()
+        for v in range(C4_POSES):
+            for (do, dp, so, sp, wb, n) in plan:
+                peer.send2d(v * frame + do, dp, base + v * rows * row + so, sp, wb, n, comm.cuda_stream)
+        ev = torch.cuda.Event()
+        ev.record(comm)
+        sent[k] = ev
+
+    def sync_all():
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(comm)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    cs = ClockSampler(local_rank)
+    if rank == 0:
+        cs.start()
+    for i in range(args.warmup):
+        step(i)
+    sync_all()
+    launches0 = lib().vr_launch_count()
+    kern = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cs.begin()
+    e0.record()
+    for i in range(args.steps):
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        step(i)
+        k1.record()
+        kern.append((k0, k1))
+    if world > 1:
+        torch.cuda.current_stream().wait_stream(comm)
+    e1.record()
+    sync_all()
+    launches = lib().vr_launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    extra = 0
+    while rank == 0 and world == 1 and time.time() - cs.t0 < 1.2:
+        step(extra)
+        torch.cuda.synchronize()
+        extra += 1
+    cs.end()
+    clocks = cs.stop() if rank == 0 else None
+    kms = float(np.mean([a.elapsed_time(b) for a, b in kern]))
+    t = torch.tensor([ms_total, kms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, kms_max = float(t[0].item()) / args.steps, float(t[1].item())
+
+    # reassembly check + e2e (frames to pinned host memory on rank 0 inside the timed region)
+    identical = None
+    host = torch.empty((C4_POSES, C4_H, C4_W, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
+
+    def e2e_step(i):
+        step(i)
+        sync_all()                                 # every rank's bands have landed on rank 0
+        if rank == 0:
+            src = frames.data_ptr() if world == 1 else peer.root
+            lib().vr_copy_async(ctypes.c_void_p(host.data_ptr()), ctypes.c_void_p(src), frame * C4_POSES, None)
+            torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    e2e_step(0)
+    if rank == 0:
+        identical = bool(np.array_equal(host[::13].numpy(), solo))
+    t0 = time.perf_counter()
+    n_e2e = max(2, min(args.steps, 5))
+    for i in range(n_e2e):
+        e2e_step(i)
+    te = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+
+    if rank == 0:
+        peak, peak_note = measured_peak()
+        rays = C4_W * C4_H * C4_POSES
+        line = {
+            "metric": "Mrays/s @ 1920x1080", "value": rays / ms_step / 1e3, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_frame": ms_step / C4_POSES, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "fps": C4_POSES / ms_step * 1e3,
+            "config": {"workload": C4_WORKLOAD, "tree_depth": info["max_depth"], "nodes": info["capacity"],
+                       "tree_bytes_device": info["kernel_bytes"], "views_per_step": C4_POSES,
+                       "parallelism": f"ray tiles x{world}" + ("" if world == 1 else ", bands to rank 0 by 2-D peer copies (copy engines, NVLink)"),
+                       "kernel_variant": lib().vr_tree_variant(tree._handle), "reassembly_identical_to_single_gpu": identical,
+                       "l2": "inputs larger than L2 (1.6 GB of tables + records, a different pose every frame); no flush needed"},
+            "roofline": {"bound": "hbm", "achieved": a_step / world / (kms_max * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": a_step / world / (kms_max * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_note,
+                         "algorithmic_bytes_per_launch": a_step / world, "kernel_ms_per_launch": kms_max,
+                         "compulsory": {"bytes_per_launch": c_step / world, "achieved": c_step / world / (kms_max * 1e-3) / 1e9,
+                                        "frac": c_step / world / (kms_max * 1e-3) / 1e9 / peak},
+                         "counters": {"samples": S, "child_loads": D, "shaded": SH, "rays_hit": HIT, "node_fetches": FETCH},
+                         "note": "per GPU: 1/N of the job's algorithmic bytes (SURVEY 8d) over the slowest rank's launch time"},
+            "e2e": {"value": rays / e2e_ms / 1e3, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 64 * C4_POSES * world,
+                    "d2h_bytes_per_step": frame * C4_POSES},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        peer.close()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="config2", choices=["config2", "config4"],
+                    help="config2 (default, the headline): lego 800x800, 200 poses, weak scaling by views; "
+                         "config4: depth-11 SH25 1920x1080, strong scaling by ray tiles")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
@@ -387,6 +608,9 @@ def main():
     local_rank = env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
         reference_arm(args, rank, world)
+        return
+    if args.workload == "config4":
+        main_config4(args, rank, world, local_rank)
         return
 
     import torch

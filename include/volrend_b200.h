@@ -155,6 +155,9 @@ int vr_render_surface(const vr_tree* tree, const vr_camera* cam, const vr_option
 int vr_render_bands(const vr_tree* tree, const vr_camera* cam, const vr_options* opt, int band_h, int n_parts,
                     int part, uint8_t* rgba8_dev, float* rgba32f_dev, void* stream);
 int vr_band_rows(int height, int band_h, int n_parts, int part);
+/* Same for n_views cameras in ONE launch: view i's bands land at rgba8_dev + i * 4*width*vr_band_rows(). */
+int vr_render_bands_batch(const vr_tree* tree, const vr_camera* cams, int n_views, const vr_options* opt, int band_h,
+                          int n_parts, int part, uint8_t* rgba8_dev, float* rgba32f_dev, void* stream);
 
 /* Host-buffer entry point: renders n_views full frames and copies each to
  * rgba8_host + i*4*w*h (pinned or pageable); returns after the last copy completed. */
@@ -203,6 +206,31 @@ int vr_ipc_export(void* dev_ptr, unsigned char handle_out[64]);
 int vr_ipc_open(const unsigned char handle[64], void** ptr_out);
 int vr_ipc_close(void* ptr);
 int vr_copy_async(void* dst, const void* src, size_t bytes, void* stream);
+/* 2-D variant (cudaMemcpy2DAsync, kind inferred): scatters a rank's compact bands into their interleaved rows
+ * of a frame that lives in a peer-mapped buffer. */
+int vr_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+                    void* stream);
+
+/* ---- multi-GPU, one process driving N devices (volrend_b200/csrc/vr_mg.cu) ------------------------------
+ * What a multi-GPU main_headless.cpp needs (the reference is single-GPU: main_headless.cpp:118-121 picks ONE
+ * device): the tree replicated on `devices`, poses or ray tiles sharded over them, finished RGBA8 frames
+ * gathered on devices[0] by the copy engines over NVLink (peer copies, no SM-resident collective).
+ *   VR_MG_VIEWS  view i -> device i % n            VR_MG_TILES  band b (band_h rows) of every frame -> device b % n
+ * vr_mg_render is synchronous: on return n_views frames are in rgba8_dev0 (device memory on devices[0]; NULL =
+ * an internal buffer, see vr_mg_frames_dev0) and, when rgba8_host != NULL, in host memory.  `batch` = views per
+ * kernel launch per device (<= 0: all).  *ms_out = device time of the whole job, max over devices (CUDA events;
+ * all devices start idle). */
+typedef struct vr_mg vr_mg;
+enum { VR_MG_VIEWS = 0, VR_MG_TILES = 1 };
+int vr_mg_create(const vr_tree_desc* desc, const int* devices, int n_devices, vr_mg** out);
+void vr_mg_destroy(vr_mg* mg);
+int vr_mg_device_count(const vr_mg* mg);
+int vr_mg_device(const vr_mg* mg, int index);
+vr_tree* vr_mg_tree(const vr_mg* mg, int index);
+int vr_mg_render(vr_mg* mg, const vr_camera* cams, int n_views, const vr_options* opt, int mode, int band_h, int batch,
+                 uint8_t* rgba8_dev0, uint8_t* rgba8_host, float* ms_out);
+const uint8_t* vr_mg_frames_dev0(const vr_mg* mg);
+const char* vr_mg_last_error(const vr_mg* mg);
 /* How many of this library's kernels were launched by this process. */
 unsigned long long vr_launch_count(void);
 

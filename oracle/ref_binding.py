@@ -41,6 +41,9 @@ def lib():
         h.ref_render_f32.restype = C.c_int
         h.ref_render_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p,
                                      C.POINTER(ref_options), C.c_void_p]
+        h.ref_render_f32_composite.restype = C.c_int
+        h.ref_render_f32_composite.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p,
+                                               C.POINTER(ref_options), C.c_void_p, C.c_void_p, C.c_void_p]
         h.ref_time_frames.restype = C.c_float
         h.ref_time_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_int,
                                       C.POINTER(ref_options), C.c_int, C.c_void_p]
@@ -94,10 +97,15 @@ class RefTree:
             raise RuntimeError(f"ref_render_u8 failed {rc}")
         return out
 
-    def render_f32(self, w, h, fx, fy, c2w12, opt) -> np.ndarray:
+    def render_f32(self, w, h, fx, fy, c2w12, opt, rgba_in=None, depth_in=None) -> np.ndarray:
         out = np.zeros((h, w, 4), np.float32)
         c = np.ascontiguousarray(c2w12, np.float32)
-        rc = lib().ref_render_f32(self.h, w, h, fx, fy, c.ctypes.data, C.byref(opt), out.ctypes.data)
+        if rgba_in is not None:
+            rin, din = np.ascontiguousarray(rgba_in, np.uint8), np.ascontiguousarray(depth_in, np.float32)
+            rc = lib().ref_render_f32_composite(self.h, w, h, fx, fy, c.ctypes.data, C.byref(opt), rin.ctypes.data,
+                                                din.ctypes.data, out.ctypes.data)
+        else:
+            rc = lib().ref_render_f32(self.h, w, h, fx, fy, c.ctypes.data, C.byref(opt), out.ctypes.data)
         if rc:
             raise RuntimeError(f"ref_render_f32 failed {rc}")
         return out

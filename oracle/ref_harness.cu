@@ -26,10 +26,16 @@ namespace volrend {
 namespace device {
 // Float tap: same statements as render_kernel (volrend.cu:136-158, offscreen branch), storing
 // out[4] instead of truncating to bytes (volrend.cu:166).
-__global__ static void tap_kernel(CameraSpec cam, TreeSpec tree, RenderOptions opt, float4* out4) {
+__global__ static void tap_kernel(CameraSpec cam, TreeSpec tree, RenderOptions opt, float4* out4,
+                                  const uint8_t* rgba_in = nullptr, const float* depth_in = nullptr) {
     CUDA_GET_THREAD_ID(idx, cam.width * cam.height);
     const int x = idx % cam.width, y = idx / cam.width;
     float dir[3], cen[3], out[4];
+    const bool offscreen = rgba_in == nullptr;   // volrend.cu:90-96: existing colour for compositing
+    uint8_t rgbx_init[4] = {0, 0, 0, 0};
+    if (!offscreen) {
+        for (int i = 0; i < 4; ++i) rgbx_init[i] = rgba_in[4 * idx + i];
+    }
     out[0] = out[1] = out[2] = out[3] = 0.f;
     if (tree.N > 0) {
         screen2worlddir(x, y, cam, dir, cen);
@@ -39,14 +45,21 @@ __global__ static void tap_kernel(CameraSpec cam, TreeSpec tree, RenderOptions o
             cen[i] = tree.offset[i] + tree.scale[i] * cen[i];
         }
         float t_max = 1e9f;
+        if (!offscreen) t_max = depth_in[idx];   // volrend.cu:143-146
         rodrigues(opt.rot_dirs, vdir);
         trace_ray(tree, dir, vdir, cen, opt, t_max, out);
     }
     const float nalpha = 1.f - out[3];
-    const float remain = opt.background_brightness * nalpha;
-    out[0] += remain;
-    out[1] += remain;
-    out[2] += remain;
+    if (offscreen) {
+        const float remain = opt.background_brightness * nalpha;
+        out[0] += remain;
+        out[1] += remain;
+        out[2] += remain;
+    } else {   // volrend.cu:159-163
+        out[0] += rgbx_init[0] / 255.f * nalpha;
+        out[1] += rgbx_init[1] / 255.f * nalpha;
+        out[2] += rgbx_init[2] / 255.f * nalpha;
+    }
     out4[idx] = make_float4(out[0], out[1], out[2], out[3]);
 }
 }  // namespace device
@@ -138,6 +151,30 @@ int ref_render_f32(void* tp, int w, int h, float fx, float fy, const float* c2w1
     cuda(Memcpy(out_host, d_out, sizeof(float4) * w * h, cudaMemcpyDeviceToHost));
     cudaError_t e = cudaGetLastError();
     cuda(Free(d_out));
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
+// Float tap of the non-offscreen branch (existing colour + per-pixel depth limit, volrend.cu:92-96,143-163).
+int ref_render_f32_composite(void* tp, int w, int h, float fx, float fy, const float* c2w12, const ref_options* o,
+                             const uint8_t* rgba_in, const float* depth_in, float* out_host) {
+    N3Tree& tree = *static_cast<N3Tree*>(tp);
+    Camera cam(w, h, fx, fy);
+    set_cam(cam, c2w12);
+    RenderOptions opt = to_opts(o);
+    float4* d_out = nullptr;
+    uint8_t* d_rgba = nullptr;
+    float* d_depth = nullptr;
+    cuda(Malloc((void**)&d_out, sizeof(float4) * w * h));
+    cuda(Malloc((void**)&d_rgba, (size_t)4 * w * h));
+    cuda(Malloc((void**)&d_depth, sizeof(float) * w * h));
+    cuda(Memcpy(d_rgba, rgba_in, (size_t)4 * w * h, cudaMemcpyHostToDevice));
+    cuda(Memcpy(d_depth, depth_in, sizeof(float) * w * h, cudaMemcpyHostToDevice));
+    const int N_CUDA_THREADS = 320;
+    const int blocks = N_BLOCKS_NEEDED(w * h, N_CUDA_THREADS);
+    device::tap_kernel<<<blocks, N_CUDA_THREADS>>>(cam, tree, opt, d_out, d_rgba, d_depth);
+    cuda(Memcpy(out_host, d_out, sizeof(float4) * w * h, cudaMemcpyDeviceToHost));
+    cudaError_t e = cudaGetLastError();
+    cuda(Free(d_out)); cuda(Free(d_rgba)); cuda(Free(d_depth));
     return e == cudaSuccess ? 0 : -(int)e;
 }
 

@@ -5,7 +5,19 @@ import numpy as np
 from volrend_b200 import synth
 
 CASES = ["cfg1_sh1", "lego_sh16", "drums_sh9", "lego_sh25_bbox", "lego_sh4_stop0", "lego_rgba",
-         "lego_sg9_rot", "lego_sh16_ndc", "lego_sh9_depth"]
+         "lego_sg9_rot", "lego_sh16_ndc", "lego_sh9_depth", "lego_asg4", "lego_sh9_composite"]
+
+
+def composite_inputs(name: str, W: int, H: int):
+    """Existing colour + per-pixel depth limit of the launch_renderer(offscreen=false) cases
+    (volrend.cu:92-96,143-163); None for offscreen cases."""
+    if name != "lego_sh9_composite":
+        return None
+    rng = np.random.default_rng(21)
+    rgba = rng.integers(0, 256, (H, W, 4)).astype(np.uint8)
+    depth = rng.uniform(2.0, 5.5, (H, W)).astype(np.float32)     # world units; cuts some rays inside the object
+    depth[: H // 4] = 1e9                                        # a band without a depth limit
+    return rgba, depth
 
 
 def build_case(name: str):
@@ -36,4 +48,9 @@ def build_case(name: str):
         return st, 64, 48, pose, {}, (64.0, 48.0, 60.0)
     if name == "lego_sh9_depth":
         return synth.make_tree("lego", depth=5, basis_dim=9, seed=18), 64, 48, poses[4], dict(render_depth=1), None
+    if name == "lego_asg4":
+        # anisotropic spherical gaussians (lumisphere.hpp:14-28), lobes in extra_data
+        return synth.make_tree("lego", depth=5, basis_dim=4, fmt="ASG", seed=19), 64, 48, poses[0], {}, None
+    if name == "lego_sh9_composite":
+        return synth.make_tree("lego", depth=5, basis_dim=9, seed=20), 64, 48, poses[3], {}, None
     raise KeyError(name)

@@ -88,3 +88,20 @@ def test_tile_and_view_sharding_reassemble_bit_exact(built, world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok_tiles and ok_views
+
+
+def test_band_scatter_plan_reassembles_frames():
+    """The 2-D copy plan of the peer-copy gather (no GPU needed: the copies are emulated with numpy strides)."""
+    rng = np.random.default_rng(0)
+    for (W, H, bh) in ((16, 48, 8), (20, 36, 8), (8, 1080, 8), (12, 17, 4), (4, 8, 16)):
+        full = rng.integers(0, 256, (H, W, 4)).astype(np.uint8)
+        for world in (1, 2, 3, 8):
+            out = np.zeros(H * W * 4, np.uint8)
+            for rank in range(world):
+                rows = [full[y0:y0 + h] for (_, y0, _, h) in vd.shard_bands(W, H, rank, world, bh)]
+                compact = (np.concatenate(rows, 0) if rows else np.zeros((0, W, 4), np.uint8)).reshape(-1)
+                assert compact.size == vd.band_rows(H, bh, world, rank) * W * 4
+                for (do, dp, so, sp, wb, n) in vd.band_scatter_plan(W, H, bh, world, rank):
+                    for r in range(n):
+                        out[do + r * dp: do + r * dp + wb] = compact[so + r * sp: so + r * sp + wb]
+            assert np.array_equal(out.reshape(H, W, 4), full), (W, H, bh, world)

@@ -146,12 +146,14 @@ def test_oracle_matches_reference_kernel_golden(built, path):
     """Pins the oracle: float RGBA of the reference's CUDA kernel (run on the B200) vs ours here.
     Positions/leaves are bit-identical; colours differ only by expf ulps => 2e-6 bound, bytes equal
     except where truncation sits on an integer boundary."""
-    from golden_cases import build_case
+    from golden_cases import build_case, composite_inputs
     z = np.load(path, allow_pickle=False)
     st, W, H, pose, optkw, ndc = build_case(str(z["case"]))
     t = ob.OracleTree.from_synth(st, ndc=ndc)
     cam = cam_for(W, H, pose)
-    f, u, _ = ob.render(t, cam, ob.make_options(**optkw))
+    comp = composite_inputs(str(z["case"]), W, H)       # launch_renderer(offscreen=false) cases
+    rin, din = comp if comp is not None else (None, None)
+    f, u, _ = ob.render(t, cam, ob.make_options(**optkw), rgba_in=rin, depth_in=din)
     ref_f, ref_u = z["ref_f32"], z["ref_u8"]
     assert f.shape == ref_f.shape
     assert np.abs(f - ref_f).max() <= 2e-6

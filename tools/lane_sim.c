@@ -20,6 +20,8 @@ typedef struct {
     uint8_t hit;
 } ray_t;
 
+static double g_act_hist[33];
+static int g_b[32];   /* cumulative levels resolved after table k */
 static uint8_t* g_trace;  /* per sample: fetches (low 4 bits) | shaded << 7 */
 static size_t g_trace_n, g_trace_cap;
 
@@ -89,8 +91,11 @@ static void trace_one(const orc_tree* tree, const orc_camera* cam, const orc_opt
         /* wide-table fetches (vr_march.cuh find_leaf_wide) */
         const uint32_t diff = (u[0] ^ pu[0]) | (u[1] ^ pu[1]) | (u[2] ^ pu[2]);
         int common = diff ? (__builtin_clz(diff) - 8) : 24;
-        int j0 = (common < pdepth - 1 ? common : pdepth - 1) >> 1;
-        int jl = (depth - 1) >> 1;
+        /* table k covers the levels (g_b[k-1], g_b[k]] and hangs off a node of depth g_b[k-1] (LEVELS / PHASE env) */
+        int shared = common < pdepth - 1 ? common : pdepth - 1;   /* deepest node depth shared and on the previous path */
+        int j0 = 0, jl = 0;
+        while (g_b[j0] <= shared) ++j0;        /* table j0 is rooted at depth g_b[j0-1] <= shared */
+        while (g_b[jl] < depth) ++jl;
         int fetches = jl - j0 + 1;
         if (fetches < 1) fetches = 1;
         pu[0] = u[0]; pu[1] = u[1]; pu[2] = u[2]; pdepth = depth;
@@ -153,6 +158,7 @@ static void sim_tiles(const ray_t* rays, int W, int H, int shared_queue, stats_t
                 }
                 S->instr += C_BODY + C_FETCH * (maxf - 1);
                 S->body_iters += 1; S->body_lanes += act;
+                if (!shared_queue) g_act_hist[act]++;
                 for (int k = 1; k < maxf; ++k) { S->fetch_iters += 1; S->fetch_lanes += fl[k]; }
                 if (nsh) {
                     if (!shared_queue) {
@@ -256,6 +262,11 @@ int main(int argc, char** argv) {
     if (fread(sigma, 2, (size_t)cap * 8, f) != (size_t)cap * 8) return 1;
     if (fread(cams, 4, (size_t)ncam * 12, f) != (size_t)ncam * 12) return 1;
     fclose(f);
+    {
+        const int lv = getenv("LEVELS") ? atoi(getenv("LEVELS")) : 2, g0 = getenv("PHASE") ? atoi(getenv("PHASE")) : lv;
+        for (int k = 0; k < 32; ++k) g_b[k] = g0 + k * lv;
+        printf("tables: %d levels per step, root table resolves %d\n", lv, g0);
+    }
     pthread_once(&g_h2f_once, init_h2f);
     orc_tree tree;
     memset(&tree, 0, sizeof(tree));
@@ -299,6 +310,13 @@ int main(int argc, char** argv) {
     }
     printf("frames %d: samples %.2fM shaded %.3fM per frame, rays hit %.0f, rays with samples %.0f\n", ncam, nsamp / ncam / 1e6,
            nshade / ncam / 1e6, nhit / ncam, nmarch / ncam);
+    {
+        double tot = 0, cum = 0;
+        for (int a = 1; a <= 32; ++a) tot += g_act_hist[a];
+        printf("body iterations by active lanes (cumulative %%):");
+        for (int a = 1; a <= 32; ++a) { cum += g_act_hist[a]; if (a % 4 == 0) printf(" <=%d:%.1f", a, 100 * cum / tot); }
+        printf("\n");
+    }
     report("P0 tiles, inline shading", &P0, ncam);
     report("P1 tiles + shared shade queue", &P1, ncam);
     for (int k = 0; k < 6; ++k) {

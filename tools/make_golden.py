@@ -15,7 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from golden_cases import CASES, build_case  # noqa: E402
+from golden_cases import CASES, build_case, composite_inputs  # noqa: E402
 from oracle import ref_binding as rb  # noqa: E402
 from volrend_b200 import synth  # noqa: E402
 
@@ -39,7 +39,10 @@ def write_case_files(name, st, ndc, tmpdir="/tmp/golden_in"):
 def main():
     out_dir = os.path.join(ROOT, "gpurun_out", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    only = sys.argv[1:]
     for name in CASES:
+        if only and name not in only:
+            continue
         st, W, H, pose, optkw, ndc = build_case(name)
         path = write_case_files(name, st, ndc)
         rt = rb.RefTree(path)
@@ -48,8 +51,10 @@ def main():
         fx = synth.focal_for(W)
         c12 = synth.c2w_to_colmajor12(pose)
         opt = rb.make_options(**optkw)
-        f = rt.render_f32(W, H, fx, fx, c12, opt)
-        u = rt.render_u8(W, H, fx, fx, c12, opt)
+        comp = composite_inputs(name, W, H)
+        rin, din = comp if comp is not None else (None, None)
+        f = rt.render_f32(W, H, fx, fx, c12, opt, rgba_in=rin, depth_in=din)
+        u = rt.render_u8(W, H, fx, fx, c12, opt, rgba_in=rin, depth_in=din)
         rt.close()
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), case=np.array(name), ref_f32=f, ref_u8=u)
         print(name, info, "alpha mean %.3f" % f[..., 3].mean(), "rgb mean %.3f" % f[..., :3].mean(), flush=True)

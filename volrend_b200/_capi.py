@@ -83,6 +83,8 @@ SYMBOLS = {
     "vr_render_bands": (C.c_int, [C.c_void_p, C.POINTER(vr_camera), C.POINTER(vr_options), C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "vr_band_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vr_render_bands_batch": (C.c_int, [C.c_void_p, C.POINTER(vr_camera), C.c_int, C.POINTER(vr_options), C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vr_debug_trace": (C.c_int, [C.c_void_p, C.POINTER(vr_camera), C.POINTER(vr_options), C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
     "vr_set_variant": (C.c_int, [C.c_int]),
@@ -96,6 +98,16 @@ SYMBOLS = {
     "vr_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "vr_ipc_close": (C.c_int, [C.c_void_p]),
     "vr_copy_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vr_copy2d_async": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "vr_mg_create": (C.c_int, [C.POINTER(vr_tree_desc), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "vr_mg_destroy": (None, [C.c_void_p]),
+    "vr_mg_device_count": (C.c_int, [C.c_void_p]),
+    "vr_mg_device": (C.c_int, [C.c_void_p, C.c_int]),
+    "vr_mg_tree": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "vr_mg_render": (C.c_int, [C.c_void_p, C.POINTER(vr_camera), C.c_int, C.POINTER(vr_options), C.c_int, C.c_int, C.c_int,
+                               C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
+    "vr_mg_frames_dev0": (C.c_void_p, [C.c_void_p]),
+    "vr_mg_last_error": (C.c_char_p, [C.c_void_p]),
     "vr_launch_count": (C.c_ulonglong, []),
     "vr_last_error": (C.c_char_p, []),
     "vr_version": (C.c_char_p, []),

@@ -782,6 +782,32 @@ int check_common(const vr_tree* t, const vr_camera* cam, const vr_options* opt, 
 
 }  // namespace
 
+namespace {
+// Cameras of a batch go through a device ring owned by (tree, stream): no allocation on the launch path (a
+// stream-ordered pool would hand memory back to the OS at every synchronisation), and a slot is rewritten
+// only by a copy that is stream-ordered behind the launch that read it.  n_views <= kCamRing.
+int stage_cams(const vr_tree* t, const vr_camera* cams, int n_views, cudaStream_t stream, LaunchDev& P) {
+    if (n_views <= 1) return VR_OK;
+    vr_tree* mt = const_cast<vr_tree*>(t);
+    StreamRes* sr = nullptr;
+    if (int rc = stream_res(mt, stream, sr)) return rc;
+    unsigned int slot;
+    {
+        std::lock_guard<std::mutex> lk(mt->res_mu);
+        if (sr->cam_pos + (unsigned int)n_views > (unsigned int)kCamRing) sr->cam_pos = 0;  // no wrap inside a batch
+        slot = sr->cam_pos;
+        sr->cam_pos += (unsigned int)n_views;
+    }
+    std::vector<CamDev> h(n_views);
+    for (int i = 0; i < n_views; ++i) fill_cam(h[i], &cams[i]);
+    CamDev* dcams = sr->cam_ring + slot;
+    VR_CUDA(cudaMemcpyAsync(dcams, h.data(), sizeof(CamDev) * n_views, cudaMemcpyHostToDevice, stream));
+    // pageable source: the copy has been staged when cudaMemcpyAsync returns
+    P.cams = dcams;
+    return VR_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int vr_render_batch(const vr_tree* t, const vr_camera* cams, int n_views, const vr_options* opt, const vr_rect* tile,
@@ -816,49 +842,53 @@ int vr_render_batch(const vr_tree* t, const vr_camera* cams, int n_views, const 
         }
         return VR_OK;
     }
-    if (n_views > 1) {
-        // cameras go through a device ring owned by the tree (no allocation on the launch path: a
-        // stream-ordered pool would hand memory back to the OS at every synchronisation)
-        // (the ring belongs to (tree, stream): a slot is rewritten only by a copy that is stream-ordered
-        // behind the launch that read it)
-        vr_tree* mt = const_cast<vr_tree*>(t);
-        StreamRes* sr = nullptr;
-        if ((rc = stream_res(mt, stream, sr))) return rc;
-        unsigned int slot;
-        {
-            std::lock_guard<std::mutex> lk(mt->res_mu);
-            if (sr->cam_pos + (unsigned int)n_views > (unsigned int)kCamRing) sr->cam_pos = 0;  // no wrap inside a batch
-            slot = sr->cam_pos;
-            sr->cam_pos += (unsigned int)n_views;
-        }
-        std::vector<CamDev> h(n_views);
-        for (int i = 0; i < n_views; ++i) fill_cam(h[i], &cams[i]);
-        CamDev* dcams = sr->cam_ring + slot;
-        VR_CUDA(cudaMemcpyAsync(dcams, h.data(), sizeof(CamDev) * n_views, cudaMemcpyHostToDevice, stream));
-        // pageable source: the copy has been staged when cudaMemcpyAsync returns
-        P.cams = dcams;
-    }
+    if ((rc = stage_cams(t, cams, n_views, stream, P))) return rc;
     return dispatch(t, P, counters_dev != nullptr, false, stream);
+}
+
+int vr_render_bands_batch(const vr_tree* t, const vr_camera* cams, int n_views, const vr_options* opt, int band_h,
+                          int n_parts, int part, uint8_t* rgba8_dev, float* rgba32f_dev, void* stream_) {
+    if (n_views < 0) return fail(VR_EINVAL, "n_views < 0");
+    if (n_views == 0) return VR_OK;
+    vr_rect r;
+    int rc = check_common(t, cams, opt, nullptr, r);
+    if (rc) return rc;
+    if (band_h < 4 || band_h % 4 || n_parts < 1 || part < 0 || part >= n_parts)
+        return fail(VR_EINVAL, "bands: band_h must be a positive multiple of 4 and 0 <= part < n_parts");
+    for (int i = 1; i < n_views; ++i)
+        if (cams[i].width != cams[0].width || cams[i].height != cams[0].height)
+            return fail(VR_EINVAL, "all views of a batch must share one image size");
+    const int rows = vr_band_rows(cams[0].height, band_h, n_parts, part);
+    if (rows == 0) return VR_OK;
+    vr_rect rr = r;
+    rr.h = rows;
+    int max_views = kCamRing;  // camera ring size, 31-bit tile index
+    if (tile_bound(rr) * max_views > 0x7fffffffLL) max_views = (int)(0x7fffffffLL / tile_bound(rr));
+    if (n_views > max_views) {
+        const size_t part_px = (size_t)r.w * rows;
+        for (int v0 = 0; v0 < n_views; v0 += max_views) {
+            const int nv = n_views - v0 < max_views ? n_views - v0 : max_views;
+            rc = vr_render_bands_batch(t, cams + v0, nv, opt, band_h, n_parts, part, rgba8_dev ? rgba8_dev + 4 * part_px * v0 : nullptr,
+                                       rgba32f_dev ? rgba32f_dev + 4 * part_px * v0 : nullptr, stream_);
+            if (rc) return rc;
+        }
+        return VR_OK;
+    }
+    LaunchDev P{};
+    P.tree = t->dev;
+    fill_opt(P.opt, opt);
+    fill_cam(P.cam, &cams[0]);
+    P.n_views = n_views;
+    P.x0 = 0; P.y0 = 0; P.w = r.w; P.h = rows;
+    P.band_h = band_h; P.band_parts = n_parts; P.band_part = part;
+    P.rgba8 = rgba8_dev; P.rgbaf = reinterpret_cast<float4*>(rgba32f_dev);
+    if ((rc = stage_cams(t, cams, n_views, (cudaStream_t)stream_, P))) return rc;
+    return dispatch(t, P, false, false, (cudaStream_t)stream_);
 }
 
 int vr_render_bands(const vr_tree* t, const vr_camera* cam, const vr_options* opt, int band_h, int n_parts,
                     int part, uint8_t* rgba8_dev, float* rgba32f_dev, void* stream_) {
-    vr_rect r;
-    int rc = check_common(t, cam, opt, nullptr, r);
-    if (rc) return rc;
-    if (band_h < 4 || band_h % 4 || n_parts < 1 || part < 0 || part >= n_parts)
-        return fail(VR_EINVAL, "bands: band_h must be a positive multiple of 4 and 0 <= part < n_parts");
-    const int rows = vr_band_rows(cam->height, band_h, n_parts, part);
-    if (rows == 0) return VR_OK;
-    LaunchDev P{};
-    P.tree = t->dev;
-    fill_opt(P.opt, opt);
-    fill_cam(P.cam, cam);
-    P.n_views = 1;
-    P.x0 = 0; P.y0 = 0; P.w = r.w; P.h = rows;
-    P.band_h = band_h; P.band_parts = n_parts; P.band_part = part;
-    P.rgba8 = rgba8_dev; P.rgbaf = reinterpret_cast<float4*>(rgba32f_dev);
-    return dispatch(t, P, false, false, (cudaStream_t)stream_);
+    return vr_render_bands_batch(t, cam, 1, opt, band_h, n_parts, part, rgba8_dev, rgba32f_dev, stream_);
 }
 
 int vr_band_rows(int height, int band_h, int n_parts, int part) {
@@ -1019,6 +1049,13 @@ int vr_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
     if (bytes == 0) return VR_OK;
     if (!dst || !src) return fail(VR_EINVAL, "null argument");
     VR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return VR_OK;
+}
+
+int vr_copy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t rows, void* stream) {
+    if (width_bytes == 0 || rows == 0) return VR_OK;
+    if (!dst || !src) return fail(VR_EINVAL, "null argument");
+    VR_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, rows, cudaMemcpyDefault, (cudaStream_t)stream));
     return VR_OK;
 }
 

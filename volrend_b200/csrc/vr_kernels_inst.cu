@@ -9,6 +9,7 @@
 // Built only with -DVR_EXPERIMENTS (make lib SUFFIX=_exp EXTRA=-DVR_EXPERIMENTS): the measured and
 // rejected structures of round 1 -- CTA-per-tile kernel, TMA-staged top grid, deferred shading,
 // software-pipelined march, tuning knobs.
+#include <cstdlib>
 #include <mutex>
 
 #include "vr_kernels.h"
@@ -92,7 +93,9 @@ cudaError_t launch_persistent(LaunchDev& P, const LaunchCfg& cfg) {
 template <int KBD, bool COUNT, int OUT>
 cudaError_t launch_queue(LaunchDev& P, const LaunchCfg& cfg) {
     if constexpr (KBD >= 4) {
-        const size_t smem = queue_smem_bytes<KBD>(P.tree.max_depth);
+        // VR_EXTRA_SMEM: measurement knob -- pads the CTA's shared memory to move the L1/shared carve-out
+        static const size_t extra = getenv("VR_EXTRA_SMEM") ? (size_t)atoi(getenv("VR_EXTRA_SMEM")) : 0;
+        const size_t smem = queue_smem_bytes<KBD>(P.tree.max_depth) + extra;
         return launch_persistent_grid(march_queue_kernel<KBD, COUNT, OUT>, smem, P, cfg);
     } else {
         return cudaErrorInvalidValue;

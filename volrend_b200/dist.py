@@ -120,3 +120,24 @@ def render_view_sharded(render_views: Callable[[List[int]], "torch.Tensor"], n_v
         idx = shard_views(n_views, rk, world)
         out[idx] = gathered[rk][: len(idx)]
     return out
+
+
+def band_scatter_plan(width: int, height: int, band_h: int, world: int, rank: int, bytes_per_pixel: int = 4):
+    """2-D copies that move ``rank``'s compact bands (band after band, ``band_rows`` rows) to their interleaved
+    rows of a full [H, W] frame: a list of (dst_offset, dst_pitch, src_offset, src_pitch, width_bytes, rows), all in
+    bytes relative to the start of the frame / of the compact buffer.  The full-height bands are ONE strided copy
+    (row = one band); a ragged last band, when this rank owns it, is a second, contiguous one.  This is what the
+    copy engines execute (vr_copy2d_async / cudaMemcpy3DPeerAsync in vr_mg.cu), no kernel involved."""
+    row = width * bytes_per_pixel
+    band = row * band_h
+    n_bands = (height + band_h - 1) // band_h
+    owned = len(range(rank, n_bands, world))
+    ragged = height % band_h != 0 and owned > 0 and (n_bands - 1) % world == rank
+    full = owned - 1 if ragged else owned
+    plan = []
+    if full > 0:
+        plan.append((rank * band, band * world, 0, band, band, full))
+    if ragged:
+        tail = (height % band_h) * row
+        plan.append((rank * band + full * band * world, tail, full * band, tail, tail, 1))
+    return plan

@@ -254,6 +254,21 @@ class N3Tree:
         self._handle = h
         self._cuda_loaded = True
 
+    def _plain_desc(self):
+        """vr_tree_desc over the decoded host arrays (keeps them alive through the returned tuple)."""
+        d = _capi.vr_tree_desc()
+        data = np.ascontiguousarray(self.data_)
+        d.child, d.data = self.child_.ctypes.data, data.ctypes.data
+        d.extra = self.extra_.ctypes.data if self.extra_ is not None else None
+        d.capacity, d.N, d.data_dim = self.capacity, self.N, self.data_dim
+        d.format, d.basis_dim = self.data_format.format, self.data_format.basis_dim
+        for i in range(3):
+            d.offset[i] = float(self.offset[i])
+            d.scale[i] = float(self.scale[i])
+        d.use_ndc = int(self.use_ndc)
+        d.ndc_width, d.ndc_height, d.ndc_focal = self.ndc_width, self.ndc_height, self.ndc_focal
+        return d, data
+
     def free_cuda(self) -> None:
         if self._handle is not None:
             lib().vr_tree_destroy(self._handle)
@@ -393,6 +408,63 @@ def render_bands(tree: N3Tree, cam: Camera, options: RenderOptions, band_h: int,
                                 image.data_ptr() if image is not None else None,
                                 float_out.data_ptr() if float_out is not None else None, _stream_ptr(stream)))
     return lib().vr_band_rows(cam.height, int(band_h), int(n_parts), int(part))
+
+
+def render_bands_batch(tree: N3Tree, cams, options: RenderOptions, band_h: int, n_parts: int, part: int, images, *,
+                       float_out=None, stream=None) -> int:
+    """render_bands for several views in ONE launch: ``images`` uint8 [V, rows, W, 4]; returns rows."""
+    arr = _cams_array(cams)
+    o = options._as_c()
+    check(lib().vr_render_bands_batch(tree._handle, arr, len(cams), C.byref(o), int(band_h), int(n_parts), int(part),
+                                      images.data_ptr() if images is not None else None,
+                                      float_out.data_ptr() if float_out is not None else None, _stream_ptr(stream)))
+    return lib().vr_band_rows(cams[0].height, int(band_h), int(n_parts), int(part)) if len(cams) else 0
+
+
+VR_MG_VIEWS, VR_MG_TILES = 0, 1
+
+
+class MultiGpuRenderer:
+    """One process driving several GPUs (vr_mg_*, volrend_b200/csrc/vr_mg.cu): the tree replicated on
+    ``devices``, views or ray tiles sharded over them, frames gathered on ``devices[0]`` by peer copies.
+    ``tree`` is a host-loaded N3Tree (its own device copy is not used)."""
+
+    def __init__(self, tree: N3Tree, devices):
+        self.devices = [int(d) for d in devices]
+        d, keep = tree._plain_desc()
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        rc = lib().vr_mg_create(C.byref(d), arr, len(self.devices), C.byref(h))
+        del keep
+        if rc != 0:
+            raise _capi.VolrendError(rc, lib().vr_mg_last_error(None).decode("utf-8", "replace"))
+        self._h = h
+
+    def render(self, cams, options: RenderOptions, *, mode=VR_MG_VIEWS, band_h=8, batch=0, out_dev0=None, out_host=None) -> float:
+        """Renders every view; returns the device time in ms (max over devices).  ``out_dev0``: uint8 CUDA
+        tensor [V,H,W,4] on devices[0] (or None: internal buffer); ``out_host``: optional CPU array/tensor."""
+        arr = _cams_array(cams)
+        o = options._as_c()
+        ms = C.c_float(0)
+        hp = None
+        if out_host is not None:
+            hp = out_host.data_ptr() if hasattr(out_host, "data_ptr") else out_host.ctypes.data
+        rc = lib().vr_mg_render(self._h, arr, len(cams), C.byref(o), int(mode), int(band_h), int(batch),
+                                out_dev0.data_ptr() if out_dev0 is not None else None, hp, C.byref(ms))
+        if rc != 0:
+            raise _capi.VolrendError(rc, lib().vr_mg_last_error(self._h).decode("utf-8", "replace"))
+        return float(ms.value)
+
+    def close(self):
+        if self._h is not None:
+            lib().vr_mg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def render_batch(tree: N3Tree, cams, options: RenderOptions, images, *, float_out=None, counters=None,
