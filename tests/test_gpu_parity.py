@@ -16,9 +16,9 @@ from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
-QUEUE, INLINE = 7, 3 + 16 * 193     # the two product kernels (vr_kernels.h)
+QUEUE, INLINE, POOL = 7, 3 + 16 * 193, 8     # the product kernels (vr_kernels.h): shading queue, inline shading, queue + ray pool
 # round-1 experiment kernels: present only in a -DVR_EXPERIMENTS build (make lib EXTRA=-DVR_EXPERIMENTS)
-VARIANTS = [QUEUE, INLINE, 1, 2, 3, 4, 5, 6, 19, 3 + 16 * 64, 3 + 16 * 65]
+VARIANTS = [QUEUE, POOL, INLINE, 1, 2, 3, 4, 5, 6, 19, 3 + 16 * 64, 3 + 16 * 65]
 
 
 def supported(tree, variant) -> bool:
@@ -82,7 +82,7 @@ def test_matches_oracle_all_formats(built, dev_trees, name, variant):
         pytest.skip("variant not built for this basis size (experiments need -DVR_EXPERIMENTS)")
     pose = synth.config1_pose() if name == "sh1_full4" else synth.nerf_synthetic_test_poses(8)[(len(name) * 3) % 8]
     cam = make_cam(72, 56, pose)
-    f, u, cnt = gpu_render(tree, cam, RenderOptions(), variant=variant, counters=(variant in (QUEUE, INLINE, 5, 6)))   # instrumented builds of the two product kernels
+    f, u, cnt = gpu_render(tree, cam, RenderOptions(), variant=variant, counters=(variant in (QUEUE, POOL, INLINE, 5, 6)))   # instrumented builds of the two product kernels
     fo, uo, co = oracle_render(st, cam, {})
     assert np.abs(f - fo).max() <= TOL
     assert np.abs(f - fo).max() <= 2e-6          # what we actually achieve (expf ulps only)
@@ -188,7 +188,7 @@ def test_tiles_batches_and_variants_are_bit_identical(built, dev_trees):
         x0, y0, w, h = tile
         assert np.array_equal(ft, full[1][0][y0:y0 + h, x0:x0 + w]), tile
         assert np.array_equal(ut, full[1][1][y0:y0 + h, x0:x0 + w]), tile
-    for v in (QUEUE, INLINE, 1, 5):
+    for v in (QUEUE, POOL, INLINE, 1, 5):
         if not supported(tree, v):
             continue
         lib().vr_set_variant(v)
@@ -298,7 +298,7 @@ def test_full_size_properties(built):
     cams = [make_cam(800, 800, p) for p in poses]
     opt = RenderOptions()
     outs = {}
-    for v in (QUEUE, INLINE):
+    for v in (QUEUE, INLINE, POOL):
         lib().vr_set_variant(v)
         imgs = torch.zeros((len(cams), 800, 800, 4), dtype=torch.uint8, device="cuda")
         fo = torch.zeros((len(cams), 800, 800, 4), dtype=torch.float32, device="cuda")
@@ -311,6 +311,8 @@ def test_full_size_properties(built):
     f, u, cnt = outs[QUEUE]
     assert np.array_equal(f, outs[INLINE][0]) and np.array_equal(u, outs[INLINE][1])     # variant-independent
     assert cnt == outs[INLINE][2]
+    # the ray pool moves rays between warps, never changes what a ray computes
+    assert np.array_equal(f, outs[POOL][0]) and np.array_equal(u, outs[POOL][1]) and cnt == outs[POOL][2]
     assert np.isfinite(f).all() and f[..., 3].min() >= 0 and f[..., 3].max() <= 1
     assert (f[..., :3] >= 0).all() and (f[..., :3] <= 1 + 1e-5).all()         # sigmoid colours, bg <= 1
     assert np.all(u[..., 3] == 255)

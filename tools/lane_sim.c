@@ -21,6 +21,7 @@ typedef struct {
 } ray_t;
 
 static double g_act_hist[33];
+static const int g_p3_theta[6] = {4, 8, 12, 8, 8, 4}, g_p3_pat[6] = {1, 1, 1, 8, 16, 16};
 static int g_b[32];   /* cumulative levels resolved after table k */
 static uint8_t* g_trace;  /* per sample: fetches (low 4 bits) | shaded << 7 */
 static size_t g_trace_n, g_trace_cap;
@@ -122,8 +123,8 @@ static void trace_one(const orc_tree* tree, const orc_camera* cam, const orc_opt
 }
 
 /* ---- cost model (warp instructions) */
-static double C_SETUP = 330, C_OUT = 25, C_BODY = 71, C_FETCH = 16, C_SHADE = 190;
-static double C_ENQ = 10, C_DRAIN = 225, C_ACC = 10, C_VOTE = 4, C_REFILL = 90, C_BATCH_EXTRA = 40, C_TILE = 30;
+static double C_SETUP = 330, C_OUT = 25, C_BODY = 105, C_FETCH = 20, C_SHADE = 190;   /* body/fetch: SASS of the r2 queue kernel */
+static double C_ENQ = 55, C_DRAIN = 250, C_ACC = 10, C_VOTE = 4, C_REFILL = 90, C_BATCH_EXTRA = 40, C_TILE = 30;
 
 typedef struct { double instr, body_iters, body_lanes, shade_iters, shade_lanes, fetch_iters, fetch_lanes; } stats_t;
 
@@ -238,6 +239,81 @@ static void sim_refill(const ray_t* rays, int W, int H, int theta, int run, int 
     }
 }
 
+/* P3: P1 + tail parking.  When a tile has had <= theta rays alive for `patience` iterations, the warp flushes its
+ * shading queue, parks the surviving rays in a pool and takes the next tile; whenever 32 rays are parked some warp
+ * marches them as a dense pass (which may park its own tail again while the pool is not empty). */
+static double C_PARK = 70, C_RESUME = 70;
+static double g_park_events[16], g_park_rays[16], g_pool_passes[16];
+static int g_p3_cur;
+static void sim_park(const ray_t* rays, int W, int H, int theta, int patience, stats_t* S) {
+    const int TW = 4, TH = 8;
+    static const ray_t* pool[1 << 16];
+    static uint32_t pool_pos[1 << 16];
+    int npool = 0;
+    const int ntx = (W + TW - 1) / TW, nty = (H + TH - 1) / TH;
+    int tile = 0;
+    const int ntiles = ntx * nty;
+    for (;;) {
+        const ray_t* lane[32];
+        uint32_t pos[32];
+        int alive = 0, from_pool = 0;
+        if (npool >= 32 || (tile >= ntiles && npool > 0)) {
+            from_pool = 1;
+            S->instr += C_RESUME;
+            g_pool_passes[g_p3_cur] += 1;
+            for (int l = 0; l < 32; ++l) {
+                if (npool) { --npool; lane[l] = pool[npool]; pos[l] = pool_pos[npool]; ++alive; }
+                else { lane[l] = NULL; pos[l] = 0; }
+            }
+        } else if (tile < ntiles) {
+            const int tx = tile % ntx, ty = tile / ntx;
+            ++tile;
+            for (int l = 0; l < 32; ++l) {
+                int x = tx * TW + l % TW, y = ty * TH + l / TW;
+                lane[l] = (x < W && y < H) ? &rays[(size_t)y * W + x] : NULL;
+                pos[l] = 0;
+                if (lane[l] && lane[l]->n) ++alive;
+            }
+            S->instr += C_TILE + C_SETUP + C_OUT;
+        } else break;
+        int q = 0, low = 0;
+        while (alive) {
+            int act = 0, maxf = 0, nsh = 0;
+            int fl[8] = {0};
+            for (int l = 0; l < 32; ++l) {
+                if (!lane[l] || pos[l] >= lane[l]->n) continue;
+                uint8_t v = g_trace[lane[l]->off + pos[l]++];
+                int f = v & 15;
+                ++act;
+                if (f > maxf) maxf = f;
+                for (int k = 1; k < f && k < 8; ++k) fl[k]++;
+                if (v & 128) ++nsh;
+                if (pos[l] >= lane[l]->n) --alive;
+            }
+            S->instr += C_BODY + C_FETCH * (maxf - 1);
+            S->body_iters += 1; S->body_lanes += act;
+            for (int k = 1; k < maxf; ++k) { S->fetch_iters += 1; S->fetch_lanes += fl[k]; }
+            if (nsh) {
+                S->instr += C_ENQ;
+                q += nsh;
+                if (q >= 32) { S->instr += C_DRAIN + 2 * C_ACC; S->shade_iters += 1; S->shade_lanes += 32; q -= 32; }
+            }
+            low = (alive <= theta) ? low + 1 : 0;
+            const int more_work = tile < ntiles || npool > 0;
+            if (alive && low >= patience && more_work) {   /* park the tail */
+                if (q) { S->instr += C_DRAIN + 2 * C_ACC; S->shade_iters += 1; S->shade_lanes += q; q = 0; }
+                S->instr += C_PARK + (from_pool ? 0 : 0);
+                g_park_events[g_p3_cur] += 1; g_park_rays[g_p3_cur] += alive;
+                for (int l = 0; l < 32; ++l)
+                    if (lane[l] && pos[l] < lane[l]->n) { pool[npool] = lane[l]; pool_pos[npool] = pos[l]; ++npool; }
+                alive = 0;
+            }
+        }
+        if (q) { S->instr += C_DRAIN + 2 * C_ACC; S->shade_iters += 1; S->shade_lanes += q; }
+        if (from_pool) S->instr += C_OUT;
+    }
+}
+
 static void report(const char* name, const stats_t* S, int frames) {
     printf("%-34s %7.2f Minstr/frame  body %5.1f/32 (%6.2fM it)  fetch+ %5.1f/32 (%5.2fM)  shade %5.1f/32 (%5.3fM it)\n", name,
            S->instr / frames / 1e6, S->body_lanes / (S->body_iters + 1e-9), S->body_iters / frames / 1e6,
@@ -276,7 +352,8 @@ int main(int argc, char** argv) {
     orc_options opt;
     orc_default_options(&opt);
 
-    stats_t P0 = {0}, P1 = {0}, P2a[6], P2b[6];
+    stats_t P0 = {0}, P1 = {0}, P2a[6], P2b[6], P3[6];
+    memset(P3, 0, sizeof(P3));
     memset(P2a, 0, sizeof(P2a)); memset(P2b, 0, sizeof(P2b));
     const int thetas[6] = {4, 8, 12, 16, 24, 32};
     ray_t* rays = (ray_t*)malloc((size_t)W * H * sizeof(ray_t));
@@ -303,6 +380,7 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < g_trace_n; ++i) nshade += g_trace[i] >> 7;
         sim_tiles(rays, W, H, 0, &P0);
         sim_tiles(rays, W, H, 1, &P1);
+        for (int k = 0; k < 6; ++k) { g_p3_cur = k; sim_park(rays, W, H, g_p3_theta[k], g_p3_pat[k], &P3[k]); }
         for (int k = 0; k < 6; ++k) {
             sim_refill(rays, W, H, thetas[k], 64, 0, &P2a[k]);
             sim_refill(rays, W, H, thetas[k], 64, 1, &P2b[k]);
@@ -319,6 +397,12 @@ int main(int argc, char** argv) {
     }
     report("P0 tiles, inline shading", &P0, ncam);
     report("P1 tiles + shared shade queue", &P1, ncam);
+    for (int k = 0; k < 6; ++k) {
+        char nm[64];
+        snprintf(nm, sizeof nm, "P3 queue + tail parking th=%d pat=%d", g_p3_theta[k], g_p3_pat[k]);
+        report(nm, &P3[k], ncam);
+        printf("      park events %.0f/frame (%.1f rays each), pool passes %.0f/frame\n", g_park_events[k] / ncam, g_park_rays[k] / (g_park_events[k] + 1e-9), g_pool_passes[k] / ncam);
+    }
     for (int k = 0; k < 6; ++k) {
         char nm[64];
         snprintf(nm, sizeof nm, "P2 refill theta=%d, inline", thetas[k]);

@@ -32,7 +32,7 @@ std::atomic<int> g_variant{0};
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_max_ctas{0};
 // Resolved default variants (vr_kernels.h): queue kernel for >= 4 basis functions, else inline shading
-constexpr int kVariantQueue = 7, kVariantInline = 3 + 16 * 193;
+constexpr int kVariantQueue = 7, kVariantInline = 3 + 16 * 193, kVariantPool = 8;
 constexpr int kQueueSlots = 256;
 constexpr int kCamRing = 8192;  // device ring of per-view cameras for batched launches
 
@@ -70,6 +70,8 @@ struct StreamRes {
     unsigned int* queues = nullptr;  // kQueueSlots x {head, done}
     CamDev* cam_ring = nullptr;      // kCamRing entries; batches take consecutive slots
     unsigned int next_queue = 0, cam_pos = 0;
+    unsigned char* pool = nullptr;   // parked-ray stacks of the ray-pool kernel (kind 8), allocated on first use
+    size_t pool_bytes = 0;
 };
 
 struct vr_tree {
@@ -451,7 +453,7 @@ void vr_tree_destroy(vr_tree* t) {
     cudaSetDevice(t->device);
     cudaFree(t->nodes); cudaFree(t->recs); cudaFree(t->top); cudaFree(t->extra);
     cudaFree(t->wide); cudaFree(t->wslot); cudaFree(t->wrecs);
-    for (auto& kv : t->res) { cudaFree(kv.second.queues); cudaFree(kv.second.cam_ring); }
+    for (auto& kv : t->res) { cudaFree(kv.second.queues); cudaFree(kv.second.cam_ring); cudaFree(kv.second.pool); }
     for (int i = 0; i < vr_tree::HostPath::kRing; ++i) {
         cudaFree(t->host.buf[i]);
         if (t->host.rendered[i]) cudaEventDestroy(t->host.rendered[i]);
@@ -645,7 +647,7 @@ static int tree_create_impl(const vr_tree_desc* d, const vr_tree_quant_desc* q, 
     D.ndc_width = d->use_ndc ? d->ndc_width : -1.f;  // data_spec.hpp:47
     D.ndc_height = d->ndc_height; D.ndc_focal = d->ndc_focal;
     D.N = d->N; D.format = d->format; D.basis_dim = d->basis_dim; D.kbd = kbd;
-    D.rec_bytes = rec_bytes; D.max_depth = max_node_depth + 1; D.wide_p = wp;
+    D.rec_bytes = rec_bytes; D.max_depth = max_node_depth + 1; D.wide_p = wp; D.wide_entries = (uint32_t)n_entries;
     vr_tree_info& I = t->info;
     I.capacity = d->capacity; I.max_depth = D.max_depth; I.rec_bytes = rec_bytes;
     I.node_bytes = n_slots * 4; I.rec_total_bytes = n_slots * (long long)rec_bytes;
@@ -738,6 +740,25 @@ int dispatch(const vr_tree* t, LaunchDev& P, bool count, bool surface, cudaStrea
     {
         std::lock_guard<std::mutex> lk(mt->res_mu);
         cfg.queue = sr->queues + 2 * (sr->next_queue++ % kQueueSlots);
+    }
+    cfg.pool = nullptr; cfg.pool_bytes = 0;
+    if ((cfg.variant & 15) == 8) {   // ray-pool kernel: its parked-ray stacks live with the (tree, stream) resources
+        size_t need = 0;
+        switch (t->dev.kbd) {
+            case 4: need = pool_bytes_for<4>(t->num_sms, t->dev.max_depth); break;
+            case 9: need = pool_bytes_for<9>(t->num_sms, t->dev.max_depth); break;
+            case 16: need = pool_bytes_for<16>(t->num_sms, t->dev.max_depth); break;
+            case 25: need = pool_bytes_for<25>(t->num_sms, t->dev.max_depth); break;
+            default: break;
+        }
+        std::lock_guard<std::mutex> lk(mt->res_mu);
+        if (need > sr->pool_bytes) {
+            // a grow only happens before the first kind-8 launch on this stream (the size depends on the tree alone)
+            if (sr->pool) { cudaStreamSynchronize(stream); cudaFree(sr->pool); sr->pool = nullptr; sr->pool_bytes = 0; }
+            if (cudaMalloc(&sr->pool, need) == cudaSuccess) sr->pool_bytes = need;
+            else { cudaGetLastError(); sr->pool = nullptr; }   // no memory: the kernel runs without parking
+        }
+        cfg.pool = sr->pool; cfg.pool_bytes = sr->pool_bytes;
     }
     cfg.l2_window = t->wide;
     cfg.l2_window_bytes = t->l2_window_bytes;

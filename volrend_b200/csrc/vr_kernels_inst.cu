@@ -3,6 +3,7 @@
 //
 // Product kernels:
 //   kind 7           march_queue_kernel (vr_march_q.cuh): default for >= 4 basis functions
+//   kind 8           the same kernel with the ray pool (POOL = true)
 //   kind 3, tune 193 march_persistent_kernel with inline shading: default for RGBA / 1 basis
 //                    function (their shading is a handful of instructions), and the A/B partner of
 //                    the queue kernel in the parity tests and the bench
@@ -90,13 +91,21 @@ cudaError_t launch_persistent(LaunchDev& P, const LaunchCfg& cfg) {
     return launch_persistent_grid(march_persistent_kernel<KBD, TOP, COUNT, OUT, TUNE>, smem, P, cfg);
 }
 
-template <int KBD, bool COUNT, int OUT>
+template <int KBD, bool COUNT, int OUT, bool POOL = false>
 cudaError_t launch_queue(LaunchDev& P, const LaunchCfg& cfg) {
     if constexpr (KBD >= 4) {
         // VR_EXTRA_SMEM: measurement knob -- pads the CTA's shared memory to move the L1/shared carve-out
         static const size_t extra = getenv("VR_EXTRA_SMEM") ? (size_t)atoi(getenv("VR_EXTRA_SMEM")) : 0;
         const size_t smem = queue_smem_bytes<KBD>(P.tree.max_depth) + extra;
-        return launch_persistent_grid(march_queue_kernel<KBD, COUNT, OUT>, smem, P, cfg);
+        P.pool = nullptr;
+        if (POOL) {   // parked-ray stacks: one per CTA of the persistent grid
+            set_work(P, cfg);
+            // a parked ray carries its pixel as (lane slot << 26 | tile index)
+            if (P.n_tiles > (1 << 26)) return launch_queue<KBD, COUNT, OUT, false>(P, cfg);
+            const size_t need = (size_t)resident_ctas(march_queue_kernel<KBD, COUNT, OUT, POOL>, smem, cfg.num_sms) * pool_bytes_per_cta<KBD>();
+            if (cfg.pool && cfg.pool_bytes >= need) P.pool = cfg.pool;
+        }
+        return launch_persistent_grid(march_queue_kernel<KBD, COUNT, OUT, POOL>, smem, P, cfg);
     } else {
         return cudaErrorInvalidValue;
     }
@@ -133,7 +142,7 @@ template <int KBD>
 bool variant_supported(int variant) {
     if (variant == 0) return true;
     const int kind = variant & 15, tune = variant >> 4;
-    if (kind == 7) return tune == 0 && KBD >= 4;
+    if (kind == 7 || kind == 8) return tune == 0 && KBD >= 4;
     if (kind == 3 && tune == kInline) return true;
 #ifdef VR_EXPERIMENTS
     if (kind == 3) return tune == 0 || tune == 1 || tune == 2 || tune == 3 || tune == 8 || tune == 10 || tune == 16 ||
@@ -149,15 +158,18 @@ cudaError_t launch_march(LaunchDev& P, const LaunchCfg& cfg) {
     if (!variant_supported<KBD>(variant)) return cudaErrorInvalidValue;
     if (variant == 0) variant = KBD >= 4 ? 7 : 3 + 16 * kInline;
     const int kind = variant & 15, tune = variant >> 4;
-    const bool queue = kind == 7;
+    const bool queue = kind == 7 || kind == 8, pool = kind == 8;
     if (cfg.surface) {  // drop-in launch_renderer path writing the caller's cudaArray
-        return queue ? launch_queue<KBD, false, kOutSurface>(P, cfg)
+        return pool ? launch_queue<KBD, false, kOutSurface, true>(P, cfg)
+             : queue ? launch_queue<KBD, false, kOutSurface>(P, cfg)
                      : launch_persistent<KBD, false, false, kOutSurface, kInline>(P, cfg);
     }
     if (cfg.count) {  // instrumented builds
-        return queue ? launch_queue<KBD, true, kOutLinear>(P, cfg)
+        return pool ? launch_queue<KBD, true, kOutLinear, true>(P, cfg)
+             : queue ? launch_queue<KBD, true, kOutLinear>(P, cfg)
                      : launch_persistent<KBD, false, true, kOutLinear, kInline>(P, cfg);
     }
+    if (pool) return launch_queue<KBD, false, kOutLinear, true>(P, cfg);
     if (queue) return launch_queue<KBD, false, kOutLinear>(P, cfg);
     if (kind == 3 && tune == kInline) return launch_persistent<KBD, false, false, kOutLinear, kInline>(P, cfg);
 #ifdef VR_EXPERIMENTS
@@ -188,7 +200,18 @@ cudaError_t launch_march(LaunchDev& P, const LaunchCfg& cfg) {
     return cudaErrorInvalidValue;
 }
 
+template <int KBD>
+size_t pool_bytes_for(int num_sms, int max_depth) {
+    if constexpr (KBD >= 4) {
+        const size_t smem = queue_smem_bytes<KBD>(max_depth);
+        return (size_t)resident_ctas(march_queue_kernel<KBD, false, kOutLinear, true>, smem, num_sms) * pool_bytes_per_cta<KBD>();
+    } else {
+        return 0;
+    }
+}
+
 template cudaError_t launch_march<VR_KBD>(LaunchDev&, const LaunchCfg&);
+template size_t pool_bytes_for<VR_KBD>(int, int);
 template bool variant_supported<VR_KBD>(int);
 
 }  // namespace vrb

@@ -44,6 +44,7 @@ struct TreeDev {
     int32_t rec_bytes;
     int32_t max_depth;
     int32_t wide_p;     // parity of the depths whose internal nodes own a wide table (0 or 1)
+    uint32_t wide_entries;  // number of table entries (64 per table): bound of every record / table index
 };
 
 struct CamDev {
@@ -92,6 +93,7 @@ struct LaunchDev {
     uint32_t div_view_mul, div_row_mul;
     int32_t div_view_shift, div_row_shift;
     unsigned int* work_counter;         // persistent kernels: global tile queue head
+    unsigned char* pool;                // ray-pool kernels: parked-ray stacks, one per CTA (vr_march_q.cuh); nullptr = no parking
     unsigned long long* trace;          // diagnostics: per work item {start ns, end ns, smid, warp}
 };
 
