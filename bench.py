@@ -435,6 +435,8 @@ def main_config4(args, rank, world, local_rank):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     from volrend_b200 import Camera, N3Tree, RenderOptions, lib, render_bands_batch, render_batch
     from volrend_b200 import dist as vd
+    if lib().vr_set_variant(args.variant) != 0:
+        raise SystemExit(f"kernel variant {args.variant} is not built into this library")
     st, poses = config4_scene()
     tree = N3Tree.from_synth(st)
     info = tree.info()

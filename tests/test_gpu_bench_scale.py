@@ -85,7 +85,7 @@ def test_config2_bench_tree_800x800_default_kernel(built, tmp_path):
     st = synth.make_tree("lego", depth=10, basis_dim=16, seed=0)
     tree = N3Tree.from_synth(st)
     info = tree.info()
-    assert info["max_depth"] == 10 and lib().vr_tree_variant(tree._handle) == 7     # the queue kernel is the default
+    assert info["max_depth"] == 10 and lib().vr_tree_variant(tree._handle) == 7     # SH16: the queue kernel is the default
     poses = synth.nerf_synthetic_test_poses(200)
     fx = synth.focal_for(800)
     cams = [_cam(800, 800, fx, poses[i]) for i in (0, 77)]
@@ -113,6 +113,8 @@ def test_config4_sh25_depth11_1080p_and_bands(built, tmp_path):
     st = synth.make_tree("gyroid_small", depth=11, basis_dim=25, seed=0, band_cells=1.0)
     tree = N3Tree.from_synth(st)
     assert tree.info()["max_depth"] == 11 and tree.info()["kernel_basis"] == 25
+    from volrend_b200 import lib
+    assert lib().vr_tree_variant(tree._handle) == 3 + 16 * 193                     # SH25: inline shading is the default
     W, H, fx = 1920, 1080, 1500.0
     pose = synth.nerf_synthetic_test_poses(40, radius=1.6, elev_deg=25.0)[7]
     cam = _cam(W, H, fx, pose)

@@ -299,6 +299,8 @@ def test_full_size_properties(built):
     opt = RenderOptions()
     outs = {}
     for v in (QUEUE, INLINE, POOL):
+        if not supported(tree, v):
+            continue
         lib().vr_set_variant(v)
         imgs = torch.zeros((len(cams), 800, 800, 4), dtype=torch.uint8, device="cuda")
         fo = torch.zeros((len(cams), 800, 800, 4), dtype=torch.float32, device="cuda")
@@ -312,7 +314,8 @@ def test_full_size_properties(built):
     assert np.array_equal(f, outs[INLINE][0]) and np.array_equal(u, outs[INLINE][1])     # variant-independent
     assert cnt == outs[INLINE][2]
     # the ray pool moves rays between warps, never changes what a ray computes
-    assert np.array_equal(f, outs[POOL][0]) and np.array_equal(u, outs[POOL][1]) and cnt == outs[POOL][2]
+    if POOL in outs:
+        assert np.array_equal(f, outs[POOL][0]) and np.array_equal(u, outs[POOL][1]) and cnt == outs[POOL][2]
     assert np.isfinite(f).all() and f[..., 3].min() >= 0 and f[..., 3].max() <= 1
     assert (f[..., :3] >= 0).all() and (f[..., :3] <= 1 + 1e-5).all()         # sigmoid colours, bg <= 1
     assert np.all(u[..., 3] == 255)

@@ -19,6 +19,8 @@ def _cam(W, H, pose):
 def test_pool_kernel_equals_queue_kernel(built, basis, fmt):
     import torch
     from volrend_b200 import N3Tree, RenderOptions, launch_renderer, lib, render_bands, render_batch, synth
+    if not lib().vr_variant_supported(basis, 8):
+        pytest.skip("the ray-pool kernel is an experiment: build with make lib EXTRA=-DVR_EXPERIMENTS")
     st = synth.make_tree("lego", depth=8, basis_dim=basis, seed=basis, fmt=fmt)
     tree = N3Tree.from_synth(st)
     W, H = 640, 480

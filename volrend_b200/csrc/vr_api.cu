@@ -32,7 +32,7 @@ std::atomic<int> g_variant{0};
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_max_ctas{0};
 // Resolved default variants (vr_kernels.h): queue kernel for >= 4 basis functions, else inline shading
-constexpr int kVariantQueue = 7, kVariantInline = 3 + 16 * 193, kVariantPool = 8;
+constexpr int kVariantQueue = 7, kVariantInline = 3 + 16 * 193;
 constexpr int kQueueSlots = 256;
 constexpr int kCamRing = 8192;  // device ring of per-view cameras for batched launches
 
@@ -274,13 +274,14 @@ __global__ void build_wide_kernel(const uint32_t* __restrict__ nodes, const int*
     if (n >= capacity) return;
     const int d = depth[n];
     if (d < 0 || (n != 0 && ((d ^ p) & 1))) return;   // unreachable, or folded into its parent's table
-    // leaf entry = kLeafBit | (103 + leaf depth) << 23 | sigma: the exponent field of the cube size (vr_march.cuh)
+    // leaf entry = kLeafBit | (103 + leaf depth + p) << 23 | sigma: the exponent field of the cube size on the
+    // 2^(24-p) position grid (vr_march.cuh)
     const uint32_t ex = (e >> 4) & 3, ey = (e >> 2) & 3, ez = e & 3;
     const size_t o = (size_t)tid[n] * 64 + e;
     if (n == 0 && p == 1) {   // single-level root table: entry6 with shift 23 yields 0/1 per axis
         const uint32_t oct = ((ex & 1) << 2) | ((ey & 1) << 1) | (ez & 1);
         const uint32_t s1 = oct, w1 = nodes[s1];
-        if (w1 & kLeafBit) { wide[o] = kLeafBit | ((uint32_t)(103 + 1) << 23) | (w1 & 0xffffu); wslot[o] = s1; }
+        if (w1 & kLeafBit) { wide[o] = kLeafBit | ((uint32_t)(103 + 1 + p) << 23) | (w1 & 0xffffu); wslot[o] = s1; }
         else { wide[o] = tid[w1]; wslot[o] = 0xffffffffu; }
         return;
     }
@@ -288,7 +289,7 @@ __global__ void build_wide_kernel(const uint32_t* __restrict__ nodes, const int*
     const uint32_t s1 = (uint32_t)n * 8u + oct1;
     const uint32_t w1 = nodes[s1];
     if (w1 & kLeafBit) {
-        wide[o] = kLeafBit | ((uint32_t)(103 + d + 1) << 23) | (w1 & 0xffffu);
+        wide[o] = kLeafBit | ((uint32_t)(103 + d + 1 + p) << 23) | (w1 & 0xffffu);
         wslot[o] = s1;
         return;
     }
@@ -296,7 +297,7 @@ __global__ void build_wide_kernel(const uint32_t* __restrict__ nodes, const int*
     const uint32_t s2 = w1 * 8u + oct2;
     const uint32_t w2 = nodes[s2];
     if (w2 & kLeafBit) {
-        wide[o] = kLeafBit | ((uint32_t)(103 + d + 2) << 23) | (w2 & 0xffffu);
+        wide[o] = kLeafBit | ((uint32_t)(103 + d + 2 + p) << 23) | (w2 & 0xffffu);
         wslot[o] = s2;
     } else {
         wide[o] = tid[w2];
@@ -382,11 +383,11 @@ __global__ void probe_kernel(TreeDev tree, float x, float y, float z, int n_out,
     uint32_t u[3];
     for (int i = 0; i < 3; ++i) {
         p[i] = fmaxf(fminf(p[i], 1.f - 1e-6f), 0.f);
-        u[i] = __float2uint_rz(p[i] * 16777216.f);
+        u[i] = __float2uint_rz(p[i] * tree.pos_scale);
     }
     uint32_t T = 0, eidx = 0;
     for (int j = 0; j < 16; ++j) {
-        const int sh = 22 + tree.wide_p - 2 * j;
+        const int sh = 22 - 2 * j;
         eidx = T * 64u + ((((u[0] >> sh) & 3u) << 4) | (((u[1] >> sh) & 3u) << 2) | ((u[2] >> sh) & 3u));
         const uint32_t w = tree.wide[eidx];
         if (w & kLeafBit) break;
@@ -433,7 +434,7 @@ int vr_tree_variant(const vr_tree* t) {
     if (!t) return -1;
     const int v = g_variant.load();
     if (v != 0) return variant_ok(t->dev.kbd, v) ? v : -1;
-    return t->dev.kbd >= 4 ? kVariantQueue : kVariantInline;
+    return t->dev.kbd == 16 ? kVariantQueue : kVariantInline;   // see launch_march (vr_kernels_inst.cu)
 }
 unsigned long long vr_launch_count(void) { return g_launches.load(); }
 
@@ -648,6 +649,9 @@ static int tree_create_impl(const vr_tree_desc* d, const vr_tree_quant_desc* q, 
     D.ndc_height = d->ndc_height; D.ndc_focal = d->ndc_focal;
     D.N = d->N; D.format = d->format; D.basis_dim = d->basis_dim; D.kbd = kbd;
     D.rec_bytes = rec_bytes; D.max_depth = max_node_depth + 1; D.wide_p = wp; D.wide_entries = (uint32_t)n_entries;
+    D.pos_scale = wp ? 8388608.f : 16777216.f;
+    D.pos_hi = (1.f - 1e-6f) * D.pos_scale;   // exact: a power-of-two multiple of 0x3F7FFFEF
+    D.icube_bias = 0x73000000u + ((uint32_t)wp << 23);
     vr_tree_info& I = t->info;
     I.capacity = d->capacity; I.max_depth = D.max_depth; I.rec_bytes = rec_bytes;
     I.node_bytes = n_slots * 4; I.rec_total_bytes = n_slots * (long long)rec_bytes;

@@ -2,11 +2,10 @@
 // Compiled six times (RGBA, SH/SG/ASG 1, 4, 9, 16, 25) so the builds run in parallel.
 //
 // Product kernels:
-//   kind 7           march_queue_kernel (vr_march_q.cuh): default for >= 4 basis functions
-//   kind 8           the same kernel with the ray pool (POOL = true)
-//   kind 3, tune 193 march_persistent_kernel with inline shading: default for RGBA / 1 basis
-//                    function (their shading is a handful of instructions), and the A/B partner of
-//                    the queue kernel in the parity tests and the bench
+//   kind 7           march_queue_kernel (vr_march_q.cuh): default for 16 basis functions, selectable for 4, 9, 25
+//   kind 8           (VR_EXPERIMENTS) the same kernel with the ray pool (POOL = true): measured, slower
+//   kind 3, tune 193 march_persistent_kernel with inline shading: default for every other basis size, and the A/B
+//                    partner of the queue kernel in the parity tests and the bench
 // Built only with -DVR_EXPERIMENTS (make lib SUFFIX=_exp EXTRA=-DVR_EXPERIMENTS): the measured and
 // rejected structures of round 1 -- CTA-per-tile kernel, TMA-staged top grid, deferred shading,
 // software-pipelined march, tuning knobs.
@@ -142,7 +141,10 @@ template <int KBD>
 bool variant_supported(int variant) {
     if (variant == 0) return true;
     const int kind = variant & 15, tune = variant >> 4;
-    if (kind == 7 || kind == 8) return tune == 0 && KBD >= 4;
+    if (kind == 7) return tune == 0 && KBD >= 4;
+#ifdef VR_EXPERIMENTS
+    if (kind == 8) return tune == 0 && KBD >= 4;
+#endif
     if (kind == 3 && tune == kInline) return true;
 #ifdef VR_EXPERIMENTS
     if (kind == 3) return tune == 0 || tune == 1 || tune == 2 || tune == 3 || tune == 8 || tune == 10 || tune == 16 ||
@@ -156,20 +158,30 @@ template <int KBD>
 cudaError_t launch_march(LaunchDev& P, const LaunchCfg& cfg) {
     int variant = cfg.variant;
     if (!variant_supported<KBD>(variant)) return cudaErrorInvalidValue;
-    if (variant == 0) variant = KBD >= 4 ? 7 : 3 + 16 * kInline;
+    // Default per basis size, from the measurements in DESIGN.md 4 (bench tree, 200-view batches / single frames, ms):
+    //   SH4  inline 0.0849 / 0.152   queue 0.0919 / 0.146        SH9   inline 0.0866 / 0.159   queue 0.0936 / 0.149
+    //   SH16 inline 0.0977 / 0.185   queue 0.0977 / 0.152        SH25  inline 0.1185 / 0.219   queue 0.3196 / 0.392
+    // The queue pays ~30 instructions per march iteration (ballots, ring bookkeeping) for a 3x denser colour block; only
+    // with 16 basis functions does that break even in batches while winning a fifth on single frames.  With 25 its
+    // per-ray basis values (112 B) push the CTA's shared memory over the 8-CTA budget.
+    if (variant == 0) variant = KBD == 16 ? 7 : 3 + 16 * kInline;
     const int kind = variant & 15, tune = variant >> 4;
-    const bool queue = kind == 7 || kind == 8, pool = kind == 8;
+    const bool queue = kind == 7 || kind == 8;
+#ifdef VR_EXPERIMENTS
+    if (kind == 8) {   // measured and rejected: the ray-pool form of the queue kernel
+        if (cfg.surface) return launch_queue<KBD, false, kOutSurface, true>(P, cfg);
+        if (cfg.count) return launch_queue<KBD, true, kOutLinear, true>(P, cfg);
+        return launch_queue<KBD, false, kOutLinear, true>(P, cfg);
+    }
+#endif
     if (cfg.surface) {  // drop-in launch_renderer path writing the caller's cudaArray
-        return pool ? launch_queue<KBD, false, kOutSurface, true>(P, cfg)
-             : queue ? launch_queue<KBD, false, kOutSurface>(P, cfg)
+        return queue ? launch_queue<KBD, false, kOutSurface>(P, cfg)
                      : launch_persistent<KBD, false, false, kOutSurface, kInline>(P, cfg);
     }
     if (cfg.count) {  // instrumented builds
-        return pool ? launch_queue<KBD, true, kOutLinear, true>(P, cfg)
-             : queue ? launch_queue<KBD, true, kOutLinear>(P, cfg)
+        return queue ? launch_queue<KBD, true, kOutLinear>(P, cfg)
                      : launch_persistent<KBD, false, true, kOutLinear, kInline>(P, cfg);
     }
-    if (pool) return launch_queue<KBD, false, kOutLinear, true>(P, cfg);
     if (queue) return launch_queue<KBD, false, kOutLinear>(P, cfg);
     if (kind == 3 && tune == kInline) return launch_persistent<KBD, false, false, kOutLinear, kInline>(P, cfg);
 #ifdef VR_EXPERIMENTS
@@ -202,12 +214,17 @@ cudaError_t launch_march(LaunchDev& P, const LaunchCfg& cfg) {
 
 template <int KBD>
 size_t pool_bytes_for(int num_sms, int max_depth) {
+#ifndef VR_EXPERIMENTS
+    (void)num_sms; (void)max_depth;
+    return 0;
+#else
     if constexpr (KBD >= 4) {
         const size_t smem = queue_smem_bytes<KBD>(max_depth);
         return (size_t)resident_ctas(march_queue_kernel<KBD, false, kOutLinear, true>, smem, num_sms) * pool_bytes_per_cta<KBD>();
     } else {
         return 0;
     }
+#endif
 }
 
 template cudaError_t launch_march<VR_KBD>(LaunchDev&, const LaunchCfg&);

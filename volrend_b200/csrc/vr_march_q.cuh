@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
             }
             if (inb && P.tree.N > 0) {
                 float vd[3];
-                hit = ray_geometry(P.tree, P.opt, cam, px, py, tlim, R, vd);
+                hit = ray_geometry(P.tree, P.opt, cam, px, py, tlim, R, vd, P.tree.pos_scale);
                 if (hit) {  // basis values of this ray -> shared memory, bs[q][lane]
                     float B[BasisCount<KBD>::n];
                     eval_basis<KBD>(P.tree, P.opt, vd, B);
@@ -419,13 +419,13 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
                 float x, y, z;
                 uint32_t ux, uy, uz, w;
                 int depth;
-                sample_pos(R, t, x, y, z, ux, uy, uz);
+                sample_pos(R, t, x, y, z, ux, uy, uz, P.tree.pos_hi);
                 find_leaf_wide<COUNT, kTuneHint | kTuneWide | kTuneWideRecs | (kPoolPack && POOL ? kTunePackDepth : 0)>(wide, stack_a, W, ux, uy, uz, w, eidx, depth,
                                                                                                         cnt, 0, wp);
                 if (COUNT) { ++cnt.samples; cnt.child_loads += depth; }
-                const float dt = cell_delta_t<true, POOL>(R, x, y, z, ux, uy, uz, depth, step, w);
+                const float dt = cell_delta_t<true, POOL>(R, x, y, z, ux, uy, uz, depth, step, w, P.tree.icube_bias);
                 const float sigma = half_bits_to_float(w);
-                float tn = __fadd_rn(t, dt);        // :187
+                bool stop = false;
                 if (sigma > sthr) {                 // :118
                     const float att = expf_pinned(__fmul_rn(__fmul_rn(-dt, R.ds), sigma));  // :119
                     weight = __fmul_rn(T, __fsub_rn(1.f, att));                               // :120
@@ -433,9 +433,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
                     if (!want_colour) r = __fmaf_rn(t, weight, r);  // :122-123
                     shaded = want_colour;
                     T = __fmul_rn(T, att);  // :174
-                    if (T < P.opt.stop_thresh) tn = __int_as_float(0x7f800000);  // :176
+                    stop = T < P.opt.stop_thresh;   // :176
                 }
-                t = tn;
+                t = stop ? __int_as_float(0x7f800000) : __fadd_rn(t, dt);        // :187, or the early-stop marker
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, shaded);
             if (bal) {

@@ -45,6 +45,12 @@ struct TreeDev {
     int32_t max_depth;
     int32_t wide_p;     // parity of the depths whose internal nodes own a wide table (0 or 1)
     uint32_t wide_entries;  // number of table entries (64 per table): bound of every record / table index
+    // With wide_p = 1 the tables behave as if the octree hung one level below a virtual root (octant 0): leaf words
+    // carry depth + wide_p, and the march keeps positions on a 2^(24 - wide_p) grid.  The three constants below are
+    // all the kernel needs of the parity -- no per-sample arithmetic on it.
+    float pos_scale;        // 2^(24 - wide_p)
+    float pos_hi;           // (1 - 1e-6f) * pos_scale: upper clamp of a position (n3tree_query.hpp:17-19)
+    uint32_t icube_bias;    // 0x73000000 + (wide_p << 23): 1/2^depth = bits(icube_bias - (w & 0x7f800000))
 };
 
 struct CamDev {
