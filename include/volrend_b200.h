@@ -182,10 +182,10 @@ int vr_probe_lumisphere(const vr_tree* tree, const float xyz_world[3], float* ou
 int vr_debug_trace(const vr_tree* tree, const vr_camera* cam, const vr_options* opt, uint8_t* rgba8_dev,
                    vr_counters* counters_dev, unsigned long long* trace_dev, void* stream);
 
-/* Kernel variant selection for measurement.  0 = default: the shading-queue kernel (7) for trees with 16 basis
- * functions, the inline-shading kernel (3 + 16*193) for every other basis size (measured).
- * vr_get_variant returns the process-wide setting (0 unless changed), vr_tree_variant the variant a launch on `tree`
- * resolves to (-1 if the setting is not available for its basis size), vr_variant_supported whether `variant` is
+/* Kernel variant selection for measurement.  0 = default: the inline-shading kernel (3 + 16*193) for batches, the
+ * shading-queue kernel (7) for single-view launches on trees with 4, 9 or 16 basis functions (measured, DESIGN.md 4;
+ * both produce identical bits).  vr_get_variant returns the process-wide setting (0 unless changed), vr_tree_variant
+ * the variant a BATCH launch on `tree` resolves to (-1 if the setting is not available for its basis size), vr_variant_supported whether `variant` is
  * built into this library for a kernel basis of -1 (RGBA), 1, 4, 9, 16 or 25. */
 int vr_set_variant(int variant);
 int vr_get_variant(void);

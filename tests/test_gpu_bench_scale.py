@@ -85,24 +85,31 @@ def test_config2_bench_tree_800x800_default_kernel(built, tmp_path):
     st = synth.make_tree("lego", depth=10, basis_dim=16, seed=0)
     tree = N3Tree.from_synth(st)
     info = tree.info()
-    assert info["max_depth"] == 10 and lib().vr_tree_variant(tree._handle) == 7     # SH16: the queue kernel is the default
+    assert info["max_depth"] == 10 and lib().vr_tree_variant(tree._handle) == 3 + 16 * 193   # the batch default
+    # the frames below are single-view launches: they run the shading-queue kernel (the single-frame default),
+    # the batch at the end of this test runs the inline kernel -- both are compared with the reference
     poses = synth.nerf_synthetic_test_poses(200)
     fx = synth.focal_for(800)
     cams = [_cam(800, 800, fx, poses[i]) for i in (0, 77)]
     windows = [(0, 0, 64, 48), (736, 752, 64, 48), (368, 376, 64, 48), (250, 300, 48, 64)]
     frames, mode = _check_against_reference_or_oracle(st, tree, cams, tmp_path, "bench_tree", windows)
     print("config 2 parity:", mode)
-    # both product kernels agree at this size too
+    # the batch default (inline shading) and, explicitly, each product kernel on single frames: same bits
     import torch
-    from volrend_b200 import RenderOptions, launch_renderer
-    lib().vr_set_variant(3 + 16 * 193)
-    try:
-        fo = torch.zeros((800, 800, 4), dtype=torch.float32, device="cuda")
-        launch_renderer(tree, cams[1], RenderOptions(), None, None, None, True, float_out=fo)
-        torch.cuda.synchronize()
-        assert np.array_equal(fo.cpu().numpy(), frames[1][0])
-    finally:
-        lib().vr_set_variant(0)
+    from volrend_b200 import RenderOptions, launch_renderer, render_batch
+    fb = torch.zeros((2, 800, 800, 4), dtype=torch.float32, device="cuda")
+    render_batch(tree, cams, RenderOptions(), None, float_out=fb)
+    torch.cuda.synchronize()
+    assert np.array_equal(fb[0].cpu().numpy(), frames[0][0]) and np.array_equal(fb[1].cpu().numpy(), frames[1][0])
+    for v in (7, 3 + 16 * 193):
+        lib().vr_set_variant(v)
+        try:
+            fo = torch.zeros((800, 800, 4), dtype=torch.float32, device="cuda")
+            launch_renderer(tree, cams[1], RenderOptions(), None, None, None, True, float_out=fo)
+            torch.cuda.synchronize()
+            assert np.array_equal(fo.cpu().numpy(), frames[1][0]), v
+        finally:
+            lib().vr_set_variant(0)
 
 
 def test_config4_sh25_depth11_1080p_and_bands(built, tmp_path):

@@ -5,7 +5,8 @@
 //     --gpus N        devices 0..N-1 of this box (default: all visible)
 //     --mode views    pose i -> GPU i % N                                (throughput of a pose sweep)
 //            tiles    every frame cut into bands of --band rows, band b -> GPU b % N   (one frame on N GPUs)
-//     --batch K       poses per kernel launch per GPU (default: all poses of the run)
+//     --batch K       poses per batch, i.e. per kernel launch on every GPU (default: a quarter of the poses in views mode so
+//                     that copies overlap rendering, all poses in tiles mode)
 //     --reps R        timed repetitions of the whole pose list (default 1; the first, untimed pass warms up)
 //     --check         also render everything on GPU 0 alone and compare the bytes
 // The reference's loader (src/n3tree.cpp + cnpy), option parser (src/opts.cpp) and headers are used
@@ -189,7 +190,11 @@ int main(int argc, char* argv[]) {
     if (n_gpus <= 0 || n_gpus > n_visible) n_gpus = n_visible;
     const std::string mode_s = args["mode"].as<std::string>();
     const int mode = mode_s == "tiles" ? VR_MG_TILES : VR_MG_VIEWS;
-    const int band = args["band"].as<int>(), batch = args["batch"].as<int>();
+    const int band = args["band"].as<int>();
+    int batch = args["batch"].as<int>();
+    // default: pose sweeps go out in four batches, so that the copy of one batch travels while the next one renders;
+    // ray tiles are cheap to move (each GPU sends 1/N of a frame) and go out in one launch
+    if (batch <= 0 && mode == VR_MG_VIEWS && (int)trans.size() >= 8 * n_gpus) batch = ((int)trans.size() + 3) / 4;
     const int reps = args["reps"].as<int>() > 0 ? args["reps"].as<int>() : 1;
 
     vr_tree_desc d;
@@ -232,10 +237,12 @@ int main(int argc, char* argv[]) {
     float ms = 0.f, ms_sum = 0.f;
     if (vr_mg_render(mg, cams.data(), n_views, &o, mode, band, batch, nullptr, nullptr, &ms) != VR_OK) die("vr_mg_render (warm-up)", mg);
     for (int r = 0; r < reps; ++r) {
-        if (vr_mg_render(mg, cams.data(), n_views, &o, mode, band, batch, nullptr, (r == reps - 1) ? host : nullptr, &ms) != VR_OK)
-            die("vr_mg_render", mg);
+        // like the reference's timed loop without -o (main_headless.cpp:208-223): frames stay on the GPU
+        if (vr_mg_render(mg, cams.data(), n_views, &o, mode, band, batch, nullptr, nullptr, &ms) != VR_OK) die("vr_mg_render", mg);
         ms_sum += ms;
     }
+    if (host && vr_mg_render(mg, cams.data(), n_views, &o, mode, band, batch, nullptr, host, &ms) != VR_OK)   // untimed: -o / --check
+        die("vr_mg_render (read-back)", mg);
     const float ms_frame = ms_sum / reps / n_views;
     printf("%.10f ms per frame\n", ms_frame);
     printf("%.10f fps\n", 1000.f / ms_frame);

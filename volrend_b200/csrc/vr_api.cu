@@ -434,7 +434,8 @@ int vr_tree_variant(const vr_tree* t) {
     if (!t) return -1;
     const int v = g_variant.load();
     if (v != 0) return variant_ok(t->dev.kbd, v) ? v : -1;
-    return t->dev.kbd == 16 ? kVariantQueue : kVariantInline;   // see launch_march (vr_kernels_inst.cu)
+    (void)kVariantQueue;   // single-view launches of 4/9/16-basis trees use it (launch_march, vr_kernels_inst.cu)
+    return kVariantInline;
 }
 unsigned long long vr_launch_count(void) { return g_launches.load(); }
 

@@ -2,10 +2,11 @@
 // Compiled six times (RGBA, SH/SG/ASG 1, 4, 9, 16, 25) so the builds run in parallel.
 //
 // Product kernels:
-//   kind 7           march_queue_kernel (vr_march_q.cuh): default for 16 basis functions, selectable for 4, 9, 25
+//   kind 7           march_queue_kernel (vr_march_q.cuh): default for single-frame launches with 4, 9 or 16 basis
+//                    functions (launch_renderer, the CLI), selectable for batches and for 25
 //   kind 8           (VR_EXPERIMENTS) the same kernel with the ray pool (POOL = true): measured, slower
-//   kind 3, tune 193 march_persistent_kernel with inline shading: default for every other basis size, and the A/B
-//                    partner of the queue kernel in the parity tests and the bench
+//   kind 3, tune 193 march_persistent_kernel with inline shading: default for batches and for RGBA / 1 / 25 basis
+//                    functions, and the A/B partner of the queue kernel in the parity tests and the bench
 // Built only with -DVR_EXPERIMENTS (make lib SUFFIX=_exp EXTRA=-DVR_EXPERIMENTS): the measured and
 // rejected structures of round 1 -- CTA-per-tile kernel, TMA-staged top grid, deferred shading,
 // software-pipelined march, tuning knobs.
@@ -158,13 +159,14 @@ template <int KBD>
 cudaError_t launch_march(LaunchDev& P, const LaunchCfg& cfg) {
     int variant = cfg.variant;
     if (!variant_supported<KBD>(variant)) return cudaErrorInvalidValue;
-    // Default per basis size, from the measurements in DESIGN.md 4 (bench tree, 200-view batches / single frames, ms):
+    // Default, from the measurements in DESIGN.md 4 (bench tree, ms/frame in 200-view batches / single-frame launches):
     //   SH4  inline 0.0849 / 0.152   queue 0.0919 / 0.146        SH9   inline 0.0866 / 0.159   queue 0.0936 / 0.149
-    //   SH16 inline 0.0977 / 0.185   queue 0.0977 / 0.152        SH25  inline 0.1185 / 0.219   queue 0.3196 / 0.392
-    // The queue pays ~30 instructions per march iteration (ballots, ring bookkeeping) for a 3x denser colour block; only
-    // with 16 basis functions does that break even in batches while winning a fifth on single frames.  With 25 its
-    // per-ray basis values (112 B) push the CTA's shared memory over the 8-CTA budget.
-    if (variant == 0) variant = KBD == 16 ? 7 : 3 + 16 * kInline;
+    //   SH16 inline 0.0962 / 0.183   queue 0.0987 / 0.154        SH25  inline 0.1185 / 0.219   queue 0.3196 / 0.392
+    // The queue pays ~30 instructions per march iteration (ballots, ring bookkeeping) for a 3x denser colour block: a
+    // loss in batches, where other warps hide the inline block's latency, a win on single frames, where the long-ray
+    // tail of the frame is what is waited for.  With 25 basis functions its per-ray basis values (112 B) push the CTA's
+    // shared memory over the 8-CTA budget.  Both kernels produce identical bits.
+    if (variant == 0) variant = (P.n_views == 1 && KBD >= 4 && KBD <= 16) ? 7 : 3 + 16 * kInline;
     const int kind = variant & 15, tune = variant >> 4;
     const bool queue = kind == 7 || kind == 8;
 #ifdef VR_EXPERIMENTS
