@@ -243,66 +243,59 @@ __global__ void node_depth_kernel(const uint32_t* __restrict__ nodes, int* __res
     }
 }
 
-// per parity p: number of internal nodes that would own a table
+// cnt[r]: number of internal nodes whose depth is r modulo kWideLv
 __global__ void count_parity_kernel(const int* __restrict__ depth, long long capacity, unsigned long long* __restrict__ cnt) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned int c0 = 0, c1 = 0;
-    if (n < capacity && depth[n] >= 0) { c0 = !(depth[n] & 1); c1 = depth[n] & 1; }
-    c0 = __reduce_add_sync(0xffffffffu, c0);
-    c1 = __reduce_add_sync(0xffffffffu, c1);
-    if ((threadIdx.x & 31) == 0) {
-        if (c0) atomicAdd(cnt, (unsigned long long)c0);
-        if (c1) atomicAdd(cnt + 1, (unsigned long long)c1);
+    const int r = (n < capacity && depth[n] >= 0) ? depth[n] % kWideLv : -1;
+#pragma unroll
+    for (int k = 0; k < kWideLv; ++k) {
+        const unsigned int c = __reduce_add_sync(0xffffffffu, r == k ? 1u : 0u);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(cnt + k, (unsigned long long)c);
     }
 }
 
-__global__ void table_flag_kernel(const int* __restrict__ depth, long long capacity, int p, uint32_t* __restrict__ flag) {
+// a node owns a table when it is the root or its depth d has (d + v) % kWideLv == 0
+__global__ void table_flag_kernel(const int* __restrict__ depth, long long capacity, int v, uint32_t* __restrict__ flag) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= capacity) return;
     const int d = depth[n];
-    flag[n] = (d >= 0 && (n == 0 || ((d ^ p) & 1) == 0)) ? 1u : 0u;
+    flag[n] = (d >= 0 && (n == 0 || (d + v) % kWideLv == 0)) ? 1u : 0u;
 }
 
-// wide[table*64 + e]: e = (ex<<4)|(ey<<2)|ez, two octree levels per axis (high bit first level).  With
-// p = 1 the root table resolves level 1 only (entries with ex,ey,ez in {0,1}).
+// wide[table * E + e], E = 8^kWideLv: e = ex << 2*LV | ey << LV | ez holds kWideLv octree levels per axis, first level
+// in the high bit.  The tree hangs v levels below a virtual root (octant 0 each time), so the root table resolves only
+// kWideLv - v real levels: its entries with a non-zero virtual bit are never looked up.
 __global__ void build_wide_kernel(const uint32_t* __restrict__ nodes, const int* __restrict__ depth,
                                   const uint32_t* __restrict__ tid, uint32_t* __restrict__ wide,
-                                  uint32_t* __restrict__ wslot, long long capacity, int p) {
+                                  uint32_t* __restrict__ wslot, long long capacity, int v) {
+    constexpr int LV = kWideLv, M = (1 << LV) - 1;
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long n = g >> 6;
-    const int e = (int)(g & 63);
+    const long long n = g >> (3 * LV);
+    const int e = (int)(g & (kWideEntries - 1));
     if (n >= capacity) return;
     const int d = depth[n];
-    if (d < 0 || (n != 0 && ((d ^ p) & 1))) return;   // unreachable, or folded into its parent's table
-    // leaf entry = kLeafBit | (103 + leaf depth + p) << 23 | sigma: the exponent field of the cube size on the
-    // 2^(24-p) position grid (vr_march.cuh)
-    const uint32_t ex = (e >> 4) & 3, ey = (e >> 2) & 3, ez = e & 3;
-    const size_t o = (size_t)tid[n] * 64 + e;
-    if (n == 0 && p == 1) {   // single-level root table: entry6 with shift 23 yields 0/1 per axis
-        const uint32_t oct = ((ex & 1) << 2) | ((ey & 1) << 1) | (ez & 1);
-        const uint32_t s1 = oct, w1 = nodes[s1];
-        if (w1 & kLeafBit) { wide[o] = kLeafBit | ((uint32_t)(103 + 1 + p) << 23) | (w1 & 0xffffu); wslot[o] = s1; }
-        else { wide[o] = tid[w1]; wslot[o] = 0xffffffffu; }
-        return;
+    if (d < 0 || (n != 0 && (d + v) % LV != 0)) return;   // unreachable, or folded into an ancestor's table
+    // leaf entry = kLeafBit | (103 + leaf depth + v) << 23 | sigma: the exponent field of the cube size on the
+    // 2^(24-v) position grid (vr_march.cuh)
+    const uint32_t ex = (e >> (2 * LV)) & M, ey = (e >> LV) & M, ez = e & M;
+    const size_t o = (size_t)tid[n] * kWideEntries + e;
+    uint32_t node = (uint32_t)n;
+    int dn = d;
+    for (int k = (n == 0) ? v : 0; k < LV; ++k) {
+        const int sh = LV - 1 - k;
+        const uint32_t oct = (((ex >> sh) & 1u) << 2) | (((ey >> sh) & 1u) << 1) | ((ez >> sh) & 1u);
+        const uint32_t s = node * 8u + oct;
+        const uint32_t w = nodes[s];
+        if (w & kLeafBit) {
+            wide[o] = kLeafBit | ((uint32_t)(103 + dn + 1 + v) << 23) | (w & 0xffffu);
+            wslot[o] = s;
+            return;
+        }
+        node = w;
+        ++dn;
     }
-    const uint32_t oct1 = ((ex >> 1) << 2) | ((ey >> 1) << 1) | (ez >> 1);
-    const uint32_t s1 = (uint32_t)n * 8u + oct1;
-    const uint32_t w1 = nodes[s1];
-    if (w1 & kLeafBit) {
-        wide[o] = kLeafBit | ((uint32_t)(103 + d + 1 + p) << 23) | (w1 & 0xffffu);
-        wslot[o] = s1;
-        return;
-    }
-    const uint32_t oct2 = ((ex & 1) << 2) | ((ey & 1) << 1) | (ez & 1);
-    const uint32_t s2 = w1 * 8u + oct2;
-    const uint32_t w2 = nodes[s2];
-    if (w2 & kLeafBit) {
-        wide[o] = kLeafBit | ((uint32_t)(103 + d + 2 + p) << 23) | (w2 & 0xffffu);
-        wslot[o] = s2;
-    } else {
-        wide[o] = tid[w2];
-        wslot[o] = 0xffffffffu;
-    }
+    wide[o] = tid[node];
+    wslot[o] = 0xffffffffu;
 }
 
 // wrecs[entry]: padded colour record of the entry's leaf, straight from the source arrays
@@ -386,9 +379,10 @@ __global__ void probe_kernel(TreeDev tree, float x, float y, float z, int n_out,
         u[i] = __float2uint_rz(p[i] * tree.pos_scale);
     }
     uint32_t T = 0, eidx = 0;
+    constexpr uint32_t M = (1u << kWideLv) - 1u;
     for (int j = 0; j < 16; ++j) {
-        const int sh = 22 - 2 * j;
-        eidx = T * 64u + ((((u[0] >> sh) & 3u) << 4) | (((u[1] >> sh) & 3u) << 2) | ((u[2] >> sh) & 3u));
+        const int sh = (24 - kWideLv) - kWideLv * j;
+        eidx = T * (uint32_t)kWideEntries + ((((u[0] >> sh) & M) << (2 * kWideLv)) | (((u[1] >> sh) & M) << kWideLv) | ((u[2] >> sh) & M));
         const uint32_t w = tree.wide[eidx];
         if (w & kLeafBit) break;
         T = w;
@@ -577,22 +571,29 @@ static int tree_create_impl(const vr_tree_desc* d, const vr_tree_quant_desc* q, 
         max_node_depth = level + 1;
     }
 
-    // two-levels-per-step tables.  Parity: tables hang off the internal nodes of even or of odd depth
-    // (+ the root); the parity with fewer tables wins -- with the other one every table at the deepest
-    // internal level would replicate its 8 leaves 8 times (6-7x more colour-record memory on trees whose
-    // deepest leaves sit at an odd depth).
+    // kWideLv-levels-per-step tables.  Which nodes own one: those whose depth d has (d + v) % kWideLv == 0, plus the
+    // root; the v with the fewest tables wins -- with another one every table at the deepest internal level would
+    // replicate its 8 leaves 8 (or 64) times (several times more colour-record memory).
     unsigned long long* pcnt = nullptr;
-    VR_CUDA(dalloc((void**)&pcnt, 2 * sizeof(unsigned long long)));
-    VR_CUDA(cudaMemset(pcnt, 0, 2 * sizeof(unsigned long long)));
+    VR_CUDA(dalloc((void**)&pcnt, 4 * sizeof(unsigned long long)));
+    VR_CUDA(cudaMemset(pcnt, 0, 4 * sizeof(unsigned long long)));
     count_parity_kernel<<<(unsigned)((d->capacity + TB - 1) / TB), TB>>>(depth, d->capacity, pcnt);
-    unsigned long long h_pcnt[2] = {0, 0};
+    unsigned long long h_pcnt[4] = {0, 0, 0, 0};
     VR_CUDA(cudaMemcpy(h_pcnt, pcnt, sizeof(h_pcnt), cudaMemcpyDeviceToHost));
-    int wp = (h_pcnt[1] + 1 < h_pcnt[0]) ? 1 : 0;
-    if (const char* e = getenv("VR_WIDE_PARITY")) { if (e[0] == '0') wp = 0; else if (e[0] == '1') wp = 1; }
-    const unsigned long long n_tab64 = wp ? h_pcnt[1] + 1 : h_pcnt[0];
-    if (n_tab64 >= (1ull << 26)) return fail(VR_EUNSUPPORTED, "too many nodes for the wide tables");
+    int wp = 0;
+    unsigned long long n_tab64 = ~0ull;
+    for (int v = 0; v < kWideLv; ++v) {
+        if (max_node_depth + 1 + v > 24) continue;   // leaf depth + v must fit the 24-bit position grid
+        const unsigned long long nt = h_pcnt[(kWideLv - v) % kWideLv] + (v ? 1 : 0);
+        if (nt + 1 < n_tab64 || n_tab64 == ~0ull) { n_tab64 = nt; wp = v; }
+    }
+    if (const char* e = getenv("VR_WIDE_PARITY")) {
+        const int v = atoi(e);
+        if (v >= 0 && v < kWideLv && max_node_depth + 1 + v <= 24) { wp = v; n_tab64 = h_pcnt[(kWideLv - v) % kWideLv] + (v ? 1 : 0); }
+    }
+    if (n_tab64 * (unsigned long long)kWideEntries >= (1ull << 32)) return fail(VR_EUNSUPPORTED, "too many nodes for the wide tables");
     const uint32_t n_tab = (uint32_t)n_tab64;
-    const long long n_entries = (long long)n_tab * 64;
+    const long long n_entries = (long long)n_tab * kWideEntries;
     {
         uint32_t *flag = nullptr, *tid = nullptr;
         void* tmp = nullptr;
@@ -605,7 +606,7 @@ static int tree_create_impl(const vr_tree_desc* d, const vr_tree_quant_desc* q, 
         VR_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, tid, (int)d->capacity));
         VR_CUDA(cudaMalloc(&t->wide, (size_t)n_entries * 4));
         VR_CUDA(cudaMalloc(&t->wslot, (size_t)n_entries * 4));
-        const long long work = d->capacity * 64;
+        const long long work = d->capacity * (long long)kWideEntries;
         build_wide_kernel<<<(unsigned)((work + TB - 1) / TB), TB>>>(t->nodes, depth, tid, t->wide, t->wslot, d->capacity, wp);
         VR_CUDA(cudaGetLastError());
         release(flag); release(tid); release(tmp);
@@ -650,7 +651,7 @@ static int tree_create_impl(const vr_tree_desc* d, const vr_tree_quant_desc* q, 
     D.ndc_height = d->ndc_height; D.ndc_focal = d->ndc_focal;
     D.N = d->N; D.format = d->format; D.basis_dim = d->basis_dim; D.kbd = kbd;
     D.rec_bytes = rec_bytes; D.max_depth = max_node_depth + 1; D.wide_p = wp; D.wide_entries = (uint32_t)n_entries;
-    D.pos_scale = wp ? 8388608.f : 16777216.f;
+    D.pos_scale = (float)(1u << (24 - wp));
     D.pos_hi = (1.f - 1e-6f) * D.pos_scale;   // exact: a power-of-two multiple of 0x3F7FFFEF
     D.icube_bias = 0x73000000u + ((uint32_t)wp << 23);
     vr_tree_info& I = t->info;

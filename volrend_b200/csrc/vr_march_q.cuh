@@ -1,18 +1,18 @@
-// vr_march_q.cuh -- the default march kernel for SH/SG/ASG trees with >= 4 basis functions:
-// persistent warps + wide tables (vr_march.cuh) + a WARP-SHARED SHADING QUEUE.
+// vr_march_q.cuh -- the march kernel with a WARP-SHARED SHADING QUEUE (warp-level compaction of the colour work):
+// persistent warps + wide tables (vr_march.cuh) + a ballot/popc-compacted ring of shaded samples per warp.
+// Default for single-view launches on trees with 4, 9 or 16 basis functions (launch_renderer, the CLI); batches
+// default to the inline-shading kernel of vr_march.cuh (launch_march in vr_kernels_inst.cu has the numbers).
 //
-// Why (tools/lane_sim.c replays the exact sample sequence of the bench frames on the CPU and
-// counts warp instructions per scheduling policy; profiles/r02_lane_sim.txt):
-//   * with inline shading the 190-instruction colour block of rt_core.cuh:125-165 runs whenever ANY
-//     lane of the warp sits on a surface: 10.0 of 32 lanes active on the bench scene (ncu of the
-//     round-1 kernel: 10.8), 28 % of all issued instructions;
-//   * per-ray lane refill (persistent threads at ray granularity) makes that WORSE -- it destroys the
-//     spatial coherence that lets neighbouring rays reach the surface in the same iteration
-//     (6.0 of 32 lanes) and its set-up cost eats the gain of the fuller march body;
-//   * a queue shared by the warp keeps the coherent 4x8 tiles for the traversal and compacts the
-//     shading work across lanes AND iterations: 29.8 of 32 lanes, -14 % instructions, and the 96-byte
-//     record fetch (46 % of the round-1 stall samples) is waited for once per 32 shaded samples
-//     instead of once per shaded warp-iteration.
+// Why (tools/lane_sim.c replays the exact sample sequence of the bench frames on the CPU and counts warp
+// instructions per scheduling policy, profiles/r02_lane_sim.txt; ncu in profiles/r02_ncu_queue_*.txt):
+//   * with inline shading the 190-instruction colour block of rt_core.cuh:125-165 runs whenever ANY lane of the
+//     warp sits on a surface: 10.8 of 32 lanes active, 28 % of all issued instructions;
+//   * a queue shared by the warp keeps the coherent 4x8 tiles for the traversal and compacts the shading work
+//     across lanes AND iterations: 29.8 of 32 lanes in the colour block, and the 96-byte record fetch is waited
+//     for once per 32 shaded samples instead of once per shaded warp-iteration;
+//   * the price is ~30 instructions per march iteration (two votes, ring bookkeeping, a predicated body) and
+//     12 KB more shared memory per CTA (less L1).  Measured: a tie to a small loss in 200-view batches, where other
+//     warps hide the inline block's latency; 17 % faster on single frames, where the frame waits for its tail.
 //
 // How: the colour of a sample never feeds back into the traversal (transmittance, early stop and the
 // next position depend on sigma and the cell geometry only, rt_core.cuh:116-120,174-187).  So the
@@ -40,7 +40,7 @@ template <int KBD>
 struct BasisQ { static constexpr int n = (BasisCount<KBD>::n + 3) / 4; };   // float4 groups per ray
 
 __host__ __device__ inline int wide_levels(int max_depth) {
-    const int l = max_depth / 2 + 1;
+    const int l = wide_table_levels(max_depth);
     return l < 1 ? 1 : l;
 }
 

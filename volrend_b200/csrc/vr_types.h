@@ -14,6 +14,16 @@ constexpr int kTopLevel = 4;
 constexpr int kTopCells = 1 << (3 * kTopLevel);
 // Deepest leaf we accept: positions are 24-bit fixed point (fp32 mantissa).
 constexpr int kMaxTreeDepth = 23;
+// Octree levels resolved per table fetch (2: 64-entry tables, 3: 512-entry tables).  Build-time choice so that entry
+// indices are shifts by constants: make lib EXTRA=-DVR_WIDE_LV=3.
+#ifndef VR_WIDE_LV
+#define VR_WIDE_LV 2
+#endif
+constexpr int kWideLv = VR_WIDE_LV;
+constexpr int kWideEntries = 1 << (3 * kWideLv);
+static_assert(kWideLv == 2 || kWideLv == 3, "tables resolve two or three octree levels");
+// tables on a root-to-leaf path (the ancestor stack of the march kernels)
+inline __host__ __device__ int wide_table_levels(int max_depth) { return (max_depth + kWideLv - 2) / kWideLv + 1; }
 
 // Device copy of one N3Tree, re-laid-out at upload (vr_tree_create):
 //  nodes[node*8 + oct]  internal: absolute child node id (>0)
@@ -43,7 +53,7 @@ struct TreeDev {
     int32_t kbd;        // kernel basis: -1 RGBA, 1, 4, 9, 16, 25 (others collapse to 1)
     int32_t rec_bytes;
     int32_t max_depth;
-    int32_t wide_p;     // parity of the depths whose internal nodes own a wide table (0 or 1)
+    int32_t wide_p;     // v in [0, kWideLv): internal nodes of depth d with (d + v) % kWideLv == 0 own a table (+ the root)
     uint32_t wide_entries;  // number of table entries (64 per table): bound of every record / table index
     // With wide_p = 1 the tables behave as if the octree hung one level below a virtual root (octant 0): leaf words
     // carry depth + wide_p, and the march keeps positions on a 2^(24 - wide_p) grid.  The three constants below are
