@@ -24,6 +24,13 @@ algorithmic GB/s against the measured HBM peak.  Workload = BASELINE config 2 ("
             built from /root/reference by oracle/Makefile.ref) on the same tree and poses, timed
             exactly like main_headless.cpp:203-228; falls back to the CPU oracle port when that
             library is absent.
+  --workload config4   BASELINE config 4 instead: depth-11 SH25 tree, 1920x1080, 40 poses per step, STRONG scaling --
+            every rank renders its interleaved 8-row bands of all frames with one launch and the copy
+            engines scatter them into the frames on rank 0 (2-D peer copies); the reassembled frames are
+            compared with a single-GPU render (`config.reassembly_identical_to_single_gpu`).
+
+Kernels: batches (the `value` / `e2e` legs) run the inline-shading kernel, single-view launches (the `cli` leg,
+launch_renderer) the shading-queue kernel; `config.kernel_variant` names the batch kernel.
 """
 from __future__ import annotations
 

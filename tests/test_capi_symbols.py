@@ -66,6 +66,18 @@ def test_no_cpu_fallback(built):
     rc = lib().vr_tree_create(C.byref(d), C.byref(h))
     assert rc == _capi.VR_ENODEVICE
     assert b"no CPU fallback" in lib().vr_last_error()
+    # the multi-GPU entry points fail the same way, and reject nonsense before touching a device
+    mg = C.c_void_p()
+    devs = (C.c_int * 2)(0, 1)
+    assert lib().vr_mg_create(C.byref(d), devs, 2, C.byref(mg)) == _capi.VR_ENODEVICE and not mg.value
+    assert b"no CPU fallback" in lib().vr_mg_last_error(None)
+    assert lib().vr_mg_create(C.byref(d), devs, 0, C.byref(mg)) == _capi.VR_EINVAL
+    assert lib().vr_mg_device_count(None) == 0 and lib().vr_mg_device(None, 0) == -1 and not lib().vr_mg_tree(None, 0)
+    ms = C.c_float(0)
+    assert lib().vr_mg_render(None, None, 0, None, 0, 8, 0, None, None, C.byref(ms)) == _capi.VR_EINVAL
+    lib().vr_mg_destroy(None)                       # no-op
+    assert lib().vr_band_rows(1080, 8, 8, 0) == 136 and lib().vr_band_rows(1080, 8, 8, 7) == 128
+    assert sum(lib().vr_band_rows(92, 8, 3, p) for p in range(3)) == 92
 
 
 def test_product_never_imports_oracle():
