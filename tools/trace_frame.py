@@ -20,6 +20,7 @@ W = H = 800
 poses = synth.nerf_synthetic_test_poses(200)
 n_items = (W // 8) * (H // 4)
 out = {}
+os.makedirs("gpurun_out", exist_ok=True)
 for pi in (17, 120):
     cam = Camera(W, H, synth.focal_for(W), synth.focal_for(W))
     cam.set_c2w(poses[pi])
@@ -50,6 +51,7 @@ for pi in (17, 120):
                last_finishers=[dict(item=int(i), ty=int(i // (W // 8)), beg=float(beg[i]), dur=float(dur[i])) for i in np.argsort(-end)[:8]],
                longest=[dict(item=int(i), beg=float(beg[i]), dur=float(dur[i])) for i in order[:8]])
     out[f"pose{pi}"] = res
+    np.savez_compressed(f"gpurun_out/trace_frame_pose{pi}.npz", beg=beg.astype(np.float32), dur=dur.astype(np.float32), warp=t[:, 3].astype(np.int32),
+                        sm=t[:, 2].astype(np.int32))
     print(json.dumps(res)[:1500])
-os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/trace_frame.json", "w"), indent=1)

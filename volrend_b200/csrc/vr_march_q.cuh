@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
 #endif
             uint32_t eidx;
             float weight;
+            // (taking 2 or 3 samples per lane between two rounds of votes was measured: +2 % time, profiles/r02_tuning_sweeps.txt)
             if (t < R.tmax) {   // rt_core.cuh:108
                 float x, y, z;
                 uint32_t ux, uy, uz, w;
