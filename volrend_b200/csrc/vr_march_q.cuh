@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
                         lds128_a(q_warp + (qhead + sl) * kQSlotBytes, cr, cg, cb, pad);
                         r = __fadd_rn(r, __uint_as_float(cr)); g = __fadd_rn(g, __uint_as_float(cg)); b = __fadd_rn(b, __uint_as_float(cb));
                     }
+                    __syncwarp();   // every owner has read its terms before a later enqueue may reuse the window (racecheck)
                     mine_cur = mine_next;
                     mine_next = 0u;
                     qhead ^= 32u;
@@ -518,6 +519,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
                         lds128_a(q_warp + (qhead + sl) * kQSlotBytes, cr, cg, cb, pad);
                         r = __fadd_rn(r, __uint_as_float(cr)); g = __fadd_rn(g, __uint_as_float(cg)); b = __fadd_rn(b, __uint_as_float(cb));
                     }
+                    __syncwarp();
                     mine_cur = 0u; qcount = 0u; qhead = 0u;
 #ifdef VR_POOL_DEBUG
                     ++dbg_flushes;
