@@ -67,7 +67,7 @@ int rec_bytes_for(int kbd) { return kbd <= 1 ? 8 : ((3 * kbd * 2 + 15) / 16) * 1
 // stream order only: a launch that reuses a slot is ordered behind the launch that used it before, so
 // no fence is needed, and launches on different streams never share a slot.
 struct StreamRes {
-    unsigned int* queues = nullptr;  // kQueueSlots x {head, done}
+    unsigned int* queues = nullptr;  // kQueueSlots slots of kQueueSlotBytes: {head, done}, per-SM block states and locks (vr_march.cuh)
     CamDev* cam_ring = nullptr;      // kCamRing entries; batches take consecutive slots
     unsigned int next_queue = 0, cam_pos = 0;
     unsigned char* pool = nullptr;   // parked-ray stacks of the ray-pool kernel (kind 8), allocated on first use
@@ -368,6 +368,15 @@ __global__ void build_top_kernel(const uint32_t* __restrict__ nodes, uint32_t* _
     top[cell] = node;
 }
 #endif
+
+// one block per queue slot: {head, done} = 0, every SM's block state = "no block", locks free (vr_march.cuh next_item)
+__global__ void queue_init_kernel(unsigned char* slots) {
+    unsigned char* slot = slots + (size_t)blockIdx.x * kQueueSlotBytes;
+    const int i = threadIdx.x;
+    if (i < 2) reinterpret_cast<unsigned int*>(slot)[i] = 0u;
+    reinterpret_cast<unsigned long long*>(slot + kQueueStateOff)[i] = ((unsigned long long)kBlkInvalid << 32) | kBlkIdle;
+    reinterpret_cast<unsigned int*>(slot + kQueueLockOff)[i] = 0u;
+}
 
 // retrieve_cursor_lumisphere_kernel (volrend.cu:175-191): descends the wide tables.
 __global__ void probe_kernel(TreeDev tree, float x, float y, float z, int n_out, float* __restrict__ out) {
@@ -719,9 +728,12 @@ int stream_res(vr_tree* t, cudaStream_t stream, StreamRes*& out) {
     auto it = t->res.find(stream);
     if (it == t->res.end()) {
         StreamRes r;
-        VR_CUDA(cudaMalloc(&r.queues, kQueueSlots * 2 * sizeof(unsigned int)));
+        VR_CUDA(cudaMalloc(&r.queues, (size_t)kQueueSlots * kQueueSlotBytes));
         cudaError_t e = cudaMalloc(&r.cam_ring, kCamRing * sizeof(CamDev));
-        if (e == cudaSuccess) e = cudaMemset(r.queues, 0, kQueueSlots * 2 * sizeof(unsigned int));   // legacy stream: ordered before later launches
+        if (e == cudaSuccess) {   // legacy stream: ordered before later launches
+            queue_init_kernel<<<kQueueSlots, 256>>>(reinterpret_cast<unsigned char*>(r.queues));
+            e = cudaGetLastError();
+        }
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
             cudaFree(r.queues); cudaFree(r.cam_ring);
@@ -745,7 +757,7 @@ int dispatch(const vr_tree* t, LaunchDev& P, bool count, bool surface, cudaStrea
     if (int rc = stream_res(mt, stream, sr)) return rc;
     {
         std::lock_guard<std::mutex> lk(mt->res_mu);
-        cfg.queue = sr->queues + 2 * (sr->next_queue++ % kQueueSlots);
+        cfg.queue = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(sr->queues) + (size_t)(sr->next_queue++ % kQueueSlots) * kQueueSlotBytes);
     }
     cfg.pool = nullptr; cfg.pool_bytes = 0;
     if ((cfg.variant & 15) == 8) {   // ray-pool kernel: its parked-ray stacks live with the (tree, stream) resources

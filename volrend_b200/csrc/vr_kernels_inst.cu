@@ -46,13 +46,29 @@ int resident_ctas(K kernel, size_t smem, int num_sms) {
     return per_sm * num_sms;
 }
 
-void set_work(LaunchDev& P, const LaunchCfg& cfg) {
+// blocks: whether the kernel understands SM-local tile blocks (the product kernels do)
+void set_work(LaunchDev& P, const LaunchCfg& cfg, bool blocks = true) {
     P.tiles_x = (P.w + kTW - 1) / kTW;
     P.tiles_y = (P.h + kTH - 1) / kTH;
+    P.work_counter = cfg.queue;
+    // Batches can have the queue hand out blocks of 8x8 tiles, the warps of an SM sharing a block (vr_march.cuh next_item).
+    // Measured (profiles/r02_tuning_sweeps.txt): config 4 (SH25, 160-byte records, 1080p) 0.511 -> 0.498 ms/frame, config 2
+    // (SH16) 0.0961 -> 0.0967: on by default for 25 basis functions only; VR_BLOCKS=0/1 forces it.  It needs enough blocks
+    // per SM to balance (a block is ~20 us of an SM), so single frames always keep one tile per item.
+    static const int force = getenv("VR_BLOCKS") ? atoi(getenv("VR_BLOCKS")) : -1;
+    const long long bx = (P.tiles_x + kBlkW - 1) / kBlkW, by = (P.tiles_y + kBlkH - 1) / kBlkH, nb = bx * by * P.n_views;
+    const bool want = force >= 0 ? force != 0 : (P.tree.kbd == 25 && P.n_views >= 2 && nb >= 16LL * cfg.num_sms);
+    if (blocks && want && nb * kBlkTiles <= 0x7fffffffLL) {
+        P.blk_mode = 1; P.blocks_x = (int)bx; P.n_blocks = (int)nb;
+        P.n_tiles = (int)(nb * kBlkTiles);   // item ids (block * 64 + tile), incl. the tiles beyond the image edge
+        set_div((uint32_t)(bx * by), P.div_view_mul, P.div_view_shift);
+        set_div((uint32_t)bx, P.div_row_mul, P.div_row_shift);
+        return;
+    }
+    P.blk_mode = 0; P.blocks_x = 0; P.n_blocks = 0;
     P.n_tiles = P.tiles_x * P.tiles_y * P.n_views;
     set_div((uint32_t)(P.tiles_x * P.tiles_y), P.div_view_mul, P.div_view_shift);
     set_div((uint32_t)P.tiles_x, P.div_row_mul, P.div_row_shift);
-    P.work_counter = cfg.queue;
 }
 
 template <typename K>
@@ -123,7 +139,7 @@ cudaError_t launch_tile(const LaunchDev& P, const LaunchCfg& cfg) {
 template <int KBD, bool TOP, bool COUNT, int OUT>
 cudaError_t launch_deferred(LaunchDev& P, const LaunchCfg& cfg) {
     const size_t smem = deferred_smem_bytes<TOP>(P.tree.max_depth);
-    set_work(P, cfg);
+    set_work(P, cfg, false);
     int grid = resident_ctas(march_deferred_kernel<KBD, TOP, COUNT, OUT>, smem, cfg.num_sms);
     const int need = (P.n_tiles + (kBlock / 32) - 1) / (kBlock / 32);
     if (grid > need) grid = need;

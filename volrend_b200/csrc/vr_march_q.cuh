@@ -177,7 +177,8 @@ constexpr int kPoolStackQ = 3;    // quads reserved for the table-id stack (12 l
 #define VR_POOL_THETA 12
 #endif
 constexpr int kPoolTheta = VR_POOL_THETA;
-#ifdef VR_POOL_NOPACK   // bisecting aid: previous depth in its own register (then it must travel with a parked ray)
+#ifdef VR_POOL_NOPACK   // bisecting aid: previous depth in its own register instead of the top byte of W.pux (one register
+                        // more in the march loop: the kernel then spills it); it must then travel with a parked ray
 constexpr bool kPoolPack = false;
 #else
 constexpr bool kPoolPack = true;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
         R.t = 0.f; R.tmax = -1.f;
         bool hit = false;
         float t = __int_as_float(0x7fc00000), T = 1.f, r = 0.f, g = 0.f, b = 0.f;   // NaN: no ray in this lane
-        Walk W = {kPoolPack && POOL ? (104u << 24) : 0u, 0u, 0u, kWideDepthBias + 1};   // "previous leaf" of a fresh ray: depth 1
+        Walk W = {kPoolPack ? (104u << 24) : 0u, 0u, 0u, kWideDepthBias + 1};   // "previous leaf" of a fresh ray: depth 1
         bool can_park = false;    // park when 1 <= live rays <= kPoolTheta (warp-uniform)
         bool from_pool = false;
         unsigned long long t_begin = 0;
@@ -340,9 +341,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
             }
         }
         if (!from_pool) {
-            if (lane == 0) item = atomicAdd(P.work_counter, 1u);
-            item = __shfl_sync(0xffffffffu, item, 0);
-            if (item >= (unsigned int)P.n_tiles) {
+            item = next_item(P, lane);
+            if (item == kNoItem) {
                 if (POOL && pool_on) {        // tell the CTA, then look at the pool once more
                     if (lane == 0) sts_volatile(ctrl + 8, 1u);
                     __syncwarp();
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
                 uint32_t ux, uy, uz, w;
                 int depth;
                 sample_pos(R, t, x, y, z, ux, uy, uz, P.tree.pos_hi);
-                find_leaf_wide<COUNT, kTuneHint | kTuneWide | kTuneWideRecs | (kPoolPack && POOL ? kTunePackDepth : 0)>(wide, stack_a, W, ux, uy, uz, w, eidx, depth,
+                find_leaf_wide<COUNT, kTuneHint | kTuneWide | kTuneWideRecs | (kPoolPack ? kTunePackDepth : 0)>(wide, stack_a, W, ux, uy, uz, w, eidx, depth,
                                                                                                         cnt, 0, wp);
                 if (COUNT) { ++cnt.samples; cnt.child_loads += depth; }
                 const float dt = cell_delta_t<true, POOL>(R, x, y, z, ux, uy, uz, depth, step, w, P.tree.icube_bias);
@@ -650,16 +650,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
     }
     if (!dep_done) pdl_wait_predecessor();
     if (COUNT) flush_counts(cnt, P.counters);
-    // the last CTA to drain re-arms the queue for the next launch that uses this slot
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int done = atomicAdd(P.work_counter + 1, 1u);
-        if (done == gridDim.x - 1) {
-            P.work_counter[0] = 0u;
-            P.work_counter[1] = 0u;
-            __threadfence();
-        }
-    }
+    rearm_queue(P);
 }
 
 }  // namespace vrb

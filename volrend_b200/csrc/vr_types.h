@@ -88,6 +88,13 @@ inline void set_div(uint32_t d, uint32_t& mul, int32_t& shift) {
     shift = s - 1;
 }
 
+// Work queue of the persistent kernels.  One slot per launch in flight: {head, done CTAs}, then per SM id (mod 256) a
+// 64-bit block state and a 32-bit lock (SM-local tile blocks, vr_march.cuh next_item).
+constexpr int kBlkW = 8, kBlkH = 8, kBlkTiles = kBlkW * kBlkH;    // a block = 8x8 warp tiles = 32x64 pixels
+constexpr uint32_t kBlkDone = 0xfffffffdu, kBlkInvalid = 0xffffffffu;
+constexpr unsigned long long kBlkIdle = 0x80000000ull;             // low word of a state that holds no tiles
+constexpr int kQueueSlotBytes = 4096, kQueueStateOff = 64, kQueueLockOff = 64 + 256 * 8;
+
 struct LaunchDev {
     TreeDev tree;
     OptDev opt;
@@ -108,7 +115,11 @@ struct LaunchDev {
     // (set_div): q = shift < 0 ? n : umulhi(n, mul) >> shift
     uint32_t div_view_mul, div_row_mul;
     int32_t div_view_shift, div_row_shift;
-    unsigned int* work_counter;         // persistent kernels: global tile queue head
+    unsigned int* work_counter;         // persistent kernels: global work queue {head, done CTAs} (start of a queue slot)
+    // SM-local tile blocks (batches, vr_march.cuh next_item): the queue hands out BLOCKS of 8x8 warp tiles, the warps of
+    // one SM share a block, so that neighbouring tiles -- same tables, same records -- are marched at the same time on
+    // the same L1.  blk_mode 0: one tile per queue item (single frames: finest balance).
+    int32_t blk_mode, blocks_x, n_blocks;
     unsigned char* pool;                // ray-pool kernels: parked-ray stacks, one per CTA (vr_march_q.cuh); nullptr = no parking
     unsigned long long* trace;          // diagnostics: per work item {start ns, end ns, smid, warp}
 };
