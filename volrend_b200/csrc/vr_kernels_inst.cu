@@ -72,8 +72,8 @@ void set_work(LaunchDev& P, const LaunchCfg& cfg, bool blocks = true) {
 }
 
 template <typename K>
-cudaError_t launch_persistent_grid(K kernel, size_t smem, LaunchDev& P, const LaunchCfg& cfg) {
-    set_work(P, cfg);
+cudaError_t launch_persistent_grid(K kernel, size_t smem, LaunchDev& P, const LaunchCfg& cfg, bool blocks = true) {
+    set_work(P, cfg, blocks);
     int grid = resident_ctas(kernel, smem, cfg.num_sms);
     if (cfg.max_ctas > 0 && grid > cfg.max_ctas) grid = cfg.max_ctas;
     const int need = (P.n_tiles + (kBlock / 32) - 1) / (kBlock / 32);
@@ -115,13 +115,13 @@ cudaError_t launch_queue(LaunchDev& P, const LaunchCfg& cfg) {
         const size_t smem = queue_smem_bytes<KBD>(P.tree.max_depth) + extra;
         P.pool = nullptr;
         if (POOL) {   // parked-ray stacks: one per CTA of the persistent grid
-            set_work(P, cfg);
+            set_work(P, cfg, false);
             // a parked ray carries its pixel as (lane slot << 26 | tile index)
             if (P.n_tiles > (1 << 26)) return launch_queue<KBD, COUNT, OUT, false>(P, cfg);
             const size_t need = (size_t)resident_ctas(march_queue_kernel<KBD, COUNT, OUT, POOL>, smem, cfg.num_sms) * pool_bytes_per_cta<KBD>();
             if (cfg.pool && cfg.pool_bytes >= need) P.pool = cfg.pool;
         }
-        return launch_persistent_grid(march_queue_kernel<KBD, COUNT, OUT, POOL>, smem, P, cfg);
+        return launch_persistent_grid(march_queue_kernel<KBD, COUNT, OUT, POOL>, smem, P, cfg, false);   // tile queue only
     } else {
         return cudaErrorInvalidValue;
     }

@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
         R.t = 0.f; R.tmax = -1.f;
         bool hit = false;
         float t = __int_as_float(0x7fc00000), T = 1.f, r = 0.f, g = 0.f, b = 0.f;   // NaN: no ray in this lane
-        Walk W = {kPoolPack ? (104u << 24) : 0u, 0u, 0u, kWideDepthBias + 1};   // "previous leaf" of a fresh ray: depth 1
+        Walk W = {kPoolPack && POOL ? (104u << 24) : 0u, 0u, 0u, kWideDepthBias + 1};   // "previous leaf" of a fresh ray: depth 1
         bool can_park = false;    // park when 1 <= live rays <= kPoolTheta (warp-uniform)
         bool from_pool = false;
         unsigned long long t_begin = 0;
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
             }
         }
         if (!from_pool) {
-            item = next_item(P, lane);
+            item = next_item<false>(P, lane);
             if (item == kNoItem) {
                 if (POOL && pool_on) {        // tell the CTA, then look at the pool once more
                     if (lane == 0) sts_volatile(ctrl + 8, 1u);
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
                 break;
             }
             int view, tx, ty;
-            decode_item(P, item, view, tx, ty);
+            decode_item<false>(P, item, view, tx, ty);
             const int lx = tx * kTW + (lane % kTW), ly = ty * kTH + (lane / kTW);
             const bool inb = lx < P.w && ly < P.h;
             const CamDev& cam = P.cams ? P.cams[view] : P.cam;
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
                 uint32_t ux, uy, uz, w;
                 int depth;
                 sample_pos(R, t, x, y, z, ux, uy, uz, P.tree.pos_hi);
-                find_leaf_wide<COUNT, kTuneHint | kTuneWide | kTuneWideRecs | (kPoolPack ? kTunePackDepth : 0)>(wide, stack_a, W, ux, uy, uz, w, eidx, depth,
+                find_leaf_wide<COUNT, kTuneHint | kTuneWide | kTuneWideRecs | (kPoolPack && POOL ? kTunePackDepth : 0)>(wide, stack_a, W, ux, uy, uz, w, eidx, depth,
                                                                                                         cnt, 0, wp);
                 if (COUNT) { ++cnt.samples; cnt.child_loads += depth; }
                 const float dt = cell_delta_t<true, POOL>(R, x, y, z, ux, uy, uz, depth, step, w, P.tree.icube_bias);
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
         uint32_t packed;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(packed) : "r"(rs + 2u * kBlock * 16u + 12u) : "memory");
         int view, tx, ty;
-        decode_item(P, packed & 0x3ffffffu, view, tx, ty);
+        decode_item<false>(P, packed & 0x3ffffffu, view, tx, ty);
         const int lx = tx * kTW + (int)((packed >> 26) % kTW), ly = ty * kTH + (int)((packed >> 26) / kTW);
         hit = __float_as_uint(t) != 0x7fc00000u;   // lanes without a ray kept the plain NaN
         const bool write_px = packed != 0xffffffffu && lx < P.w && ly < P.h && __float_as_uint(t) != 0x7fc00001u;
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) march_queue_kernel(const _
     }
     if (!dep_done) pdl_wait_predecessor();
     if (COUNT) flush_counts(cnt, P.counters);
-    rearm_queue(P);
+    rearm_queue<false>(P);
 }
 
 }  // namespace vrb
