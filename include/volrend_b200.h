@@ -98,7 +98,8 @@ typedef struct {
     int32_t rec_bytes;               /* padded leaf-record stride */
     int64_t node_bytes, rec_total_bytes, top_bytes; /* slot-indexed layout (resident in -DVR_EXPERIMENTS builds only) */
     int32_t kernel_basis;            /* -1 RGBA, 1, 4, 9, 16, 25 */
-    int32_t wide_parity;             /* 0/1: depth parity of the nodes that own a 64-entry table */
+    int32_t wide_parity;             /* v: internal nodes of depth d with (d + v) % 2 == 0 own a 64-entry table (+ the root);
+                                        the v with fewer tables is chosen per tree (% 3 and 512 entries in VR_WIDE_LV=3 builds) */
     int64_t n_tables;
     int64_t wide_bytes, wrecs_bytes; /* 64-entry tables; colour records indexed by table entry */
     int64_t kernel_bytes;            /* what the march kernels can touch: wide_bytes + wrecs_bytes */

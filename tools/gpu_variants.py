@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from volrend_b200 import synth, N3Tree, Camera, RenderOptions, launch_renderer, render_batch, render_frames_host, lib  # noqa: E402
 from volrend_b200 import _capi  # noqa: E402
 
-variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "7,8").split(",")]
+variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "7,3091").split(",")]
 INLINE = 3 + 16 * 193
 depth = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 dev = torch.device("cuda:0")
