@@ -90,7 +90,13 @@ inline void set_div(uint32_t d, uint32_t& mul, int32_t& shift) {
 
 // Work queue of the persistent kernels.  One slot per launch in flight: {head, done CTAs}, then per SM id (mod 256) a
 // 64-bit block state and a 32-bit lock (SM-local tile blocks, vr_march.cuh next_item).
-constexpr int kBlkW = 8, kBlkH = 8, kBlkTiles = kBlkW * kBlkH;    // a block = 8x8 warp tiles = 32x64 pixels
+#ifndef VR_BLK_W
+#define VR_BLK_W 8
+#endif
+#ifndef VR_BLK_H
+#define VR_BLK_H 8
+#endif
+constexpr int kBlkW = VR_BLK_W, kBlkH = VR_BLK_H, kBlkTiles = kBlkW * kBlkH;    // a block = 8x8 warp tiles = 32x64 pixels
 constexpr uint32_t kBlkDone = 0xfffffffdu, kBlkInvalid = 0xffffffffu;
 constexpr unsigned long long kBlkIdle = 0x80000000ull;             // low word of a state that holds no tiles
 constexpr int kQueueSlotBytes = 4096, kQueueStateOff = 64, kQueueLockOff = 64 + 256 * 8;
